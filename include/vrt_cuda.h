@@ -1,0 +1,173 @@
+/* vrt_cuda.h -- C ABI of the B200-native (sm_100a) render path of the `vrt` Gaussian ray tracer.
+ *
+ * The reference has no FFI for this path: callers instantiate the header templates of src/vrt/rt.h
+ * and link libvrt.so for tile_gaussians (src/vrt/rt.cpp).  This header is the boundary a maintainer
+ * binds instead; include/vrt_cuda.hpp layers the reference's own C++ call shapes
+ * (vrt::render_image / vrt::simd_render_image / vrt::tile_gaussians) on top of it.
+ * Every entry point names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * VRT_CUDA_E_* code on failure (vrt_cuda_last_error() gives the text); nothing throws, exits or
+ * falls back to a CPU implementation -- without a CUDA device vrt_cuda_create() fails.
+ * One context drives one GPU and owns one stream; contexts are independent (one per rank).
+ */
+#ifndef VRT_CUDA_H
+#define VRT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRT_CUDA_ABI_VERSION 1
+
+/* Error codes */
+#define VRT_CUDA_OK 0
+#define VRT_CUDA_E_INVALID (-1)  /* bad argument / unsupported geometry          */
+#define VRT_CUDA_E_CUDA (-2)     /* CUDA runtime error (text in last_error)      */
+#define VRT_CUDA_E_STATE (-3)    /* call order: no Gaussians / no lists yet      */
+#define VRT_CUDA_E_NOMEM (-4)
+
+/* ---- frame flags ---------------------------------------------------------------------------- */
+/* erf variant.  AS = Abramowitz-Stegun 7.1.27 with the reference's coefficients
+ * (src/vrt/approx.cpp:90-110; what simd::erf resolves to, approx.h:110-118: modes 2-4, 6-8).
+ * EXACT = libm-erff-class accuracy (template default of the scalar path, src/vrt/rt.h:32: modes 1, 5). */
+#define VRT_CUDA_ERF_AS 0u
+#define VRT_CUDA_ERF_EXACT 1u
+#define VRT_CUDA_ERF_MASK 1u
+
+/* Which Gaussians a pixel's list holds.
+ * REFERENCE      : exactly the membership of vrt::tile_gaussians (src/vrt/rt.cpp:35-62) for the
+ *                  pixel's reference tile -- the tiled modes 5-8, literal work.
+ * REFERENCE_BOUND: that membership intersected with a conservative bound: Gaussians farther than
+ *                  bound_sigmas * sigma from every ray of the pixel's 16x16 block are dropped (their
+ *                  weight is < exp(-bound_sigmas^2 / 2)); same image within 1e-6, far less work.
+ * ALL            : every Gaussian for every pixel -- the untiled modes 1-4 (src/vrt/rt.h:227-247, 315-337).
+ * BOUND          : ALL intersected with the per-block bound. */
+#define VRT_CUDA_LIST_REFERENCE (0u << 2)
+#define VRT_CUDA_LIST_REFERENCE_BOUND (1u << 2)
+#define VRT_CUDA_LIST_ALL (2u << 2)
+#define VRT_CUDA_LIST_BOUND (3u << 2)
+#define VRT_CUDA_LIST_MASK (3u << 2)
+
+/* 8-bit quantisation: TRUNCATE = (u32)(min(c,1)*255) of the scalar entry points (rt.h:238-243, 278-283);
+ * NEAREST = round-to-nearest-even of simd::cvts in the SIMD entry points (rt.h:329-333, 373-377). */
+#define VRT_CUDA_QUANT_TRUNCATE (0u << 4)
+#define VRT_CUDA_QUANT_NEAREST (1u << 4)
+/* Alpha byte: 0xFF everywhere except the tiled SIMD entry (mode 8), which stores
+ * min(1, sum albedo.w * inner) * 255 (rt.h:373, 377). */
+#define VRT_CUDA_ALPHA_OPAQUE (0u << 5)
+#define VRT_CUDA_ALPHA_FROM_W (1u << 5)
+/* Keep every list entry's terms even when its weight underflows to exactly 0 for a whole warp
+ * (disables the warp-uniform skip; results are bit-identical either way, only the work differs). */
+#define VRT_CUDA_NO_SKIP (1u << 6)
+
+/* Flag sets reproducing the reference's modes (src/volumetric-ray-tracer/main.cpp:150-177). */
+#define VRT_CUDA_MODE1 (VRT_CUDA_ERF_EXACT | VRT_CUDA_LIST_ALL | VRT_CUDA_QUANT_TRUNCATE | VRT_CUDA_ALPHA_OPAQUE)
+#define VRT_CUDA_MODE4 (VRT_CUDA_ERF_AS | VRT_CUDA_LIST_ALL | VRT_CUDA_QUANT_NEAREST | VRT_CUDA_ALPHA_OPAQUE)
+#define VRT_CUDA_MODE5 (VRT_CUDA_ERF_EXACT | VRT_CUDA_LIST_REFERENCE | VRT_CUDA_QUANT_TRUNCATE | VRT_CUDA_ALPHA_OPAQUE)
+#define VRT_CUDA_MODE8 (VRT_CUDA_ERF_AS | VRT_CUDA_LIST_REFERENCE | VRT_CUDA_QUANT_NEAREST | VRT_CUDA_ALPHA_FROM_W)
+
+/* One frame's camera and geometry: what main.cpp:263-297 passes to tile_gaussians + the render entry. */
+typedef struct vrt_cuda_frame
+{
+    float view[16];        /* camera_t::view_matrix, column-major (src/vrt/camera.cpp:52)                 */
+    float origin[4];       /* ray origin, the `origin` argument of render_image (rt.h:228)                */
+    uint32_t width;        /* image width / height in pixels                                              */
+    uint32_t height;
+    uint32_t tiles_x;      /* reference tiles per axis (main.cpp --tiles, tw = 2/tiles_x); ignored for    */
+    uint32_t tiles_y;      /*   LIST_ALL / LIST_BOUND.  width % tiles_x == 0 and height % tiles_y == 0.   */
+    uint32_t flags;        /* VRT_CUDA_* above                                                            */
+    float bound_sigmas;    /* k of the *_BOUND list modes; <= 0 selects the default 6.0                   */
+    uint32_t row_begin;    /* render only pixel rows [row_begin, row_end); 0,0 = whole image.  Used for   */
+    uint32_t row_end;      /*   multi-GPU row bands; must be multiples of 16 (or the image height).       */
+} vrt_cuda_frame;
+
+/* What a render did.  "terms" are pixel-Gaussian evaluations: one evaluation of
+ * A_j * erf(s r_j - m_j) for one pixel, one sample point s and one occluder j (loop body rt.h:107-124). */
+typedef struct vrt_cuda_stats
+{
+    uint64_t n_gaussians;     /* scene size                                                               */
+    uint64_t n_cells;         /* lists built (reference tiles or 16x16 blocks)                            */
+    uint64_t list_entries;    /* sum over cells of list length                                            */
+    uint32_t max_list;        /* longest list                                                             */
+    uint32_t n_launches;      /* kernels launched by the last tile+render                                 */
+    double terms_listed;      /* sum over rendered pixels of 5 * n^2 for the list used (E of SURVEY 8(d)) */
+    double terms_executed;    /* terms actually evaluated (<= terms_listed: warp-uniform zero-weight skip)*/
+    float ms_tile;            /* device time of the cull/tile kernels (CUDA events)                       */
+    float ms_render;          /* device time of the render kernel(s)                                      */
+    float ms_total;           /* first kernel to last kernel / copy of the call                           */
+    float reserved;
+} vrt_cuda_stats;
+
+typedef struct vrt_cuda_ctx vrt_cuda_ctx;
+
+/* Lifetime.  `device` is the CUDA ordinal (one context per GPU / per rank). */
+int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out);
+void vrt_cuda_destroy(vrt_cuda_ctx *ctx);
+const char *vrt_cuda_last_error(const vrt_cuda_ctx *ctx); /* ctx may be NULL: error of a failed create */
+int vrt_cuda_abi_version(void);
+
+/* Scene upload: replaces gaussians_t / `staging_gaussians` handed to tile_gaussians and the render entries
+ * (main.cpp:209, 261-263).  `aos` is n records of vrt::gaussian_t (40 B each, src/vrt/types.h:195-200) in
+ * HOST memory; the _device variant takes a device pointer on the context's GPU (e.g. the receive buffer of
+ * an NCCL broadcast) and copies it device-to-device on the context's stream. */
+int vrt_cuda_set_gaussians(vrt_cuda_ctx *ctx, const float *aos, uint64_t n);
+int vrt_cuda_set_gaussians_device(vrt_cuda_ctx *ctx, const float *aos_dev, uint64_t n);
+
+/* Tile projection + culling: replaces vrt::tile_gaussians(tw, th, gaussians, view) (src/vrt/rt.cpp:29-69)
+ * with tw = 2/tiles_x, th = 2/tiles_y.  Builds the per-cell lists for `frame` on the device. */
+int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame);
+
+/* Caller-supplied lists: the drop-in for the `const tiles_t &tiles` argument of the tiled render entries
+ * (rt.h:252, 345).  `aos_concat` holds the tiles' gaussian_t records back to back (tiles_t::gaussians[t]
+ * .gaussians, row-major tiles, y outer), tile t owning records [offsets[t], offsets[t+1]).  n_tiles must be
+ * frame->tiles_x * frame->tiles_y.  The frame's list mode is ignored; the lists are used as given. */
+int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, const float *aos_concat,
+                            const uint64_t *offsets, uint64_t n_tiles);
+
+/* Read back the lists of the last vrt_cuda_tile() for membership parity with tile_gaussians: counts_out[c]
+ * = length of cell c (row-major, y outer), idx_out = concatenated Gaussian indices in list order.  Either
+ * may be NULL.  *n_cells_out / *n_entries_out receive the sizes needed. */
+int vrt_cuda_get_lists(vrt_cuda_ctx *ctx, uint32_t *counts_out, uint64_t counts_cap, uint32_t *idx_out,
+                       uint64_t idx_cap, uint64_t *n_cells_out, uint64_t *n_entries_out);
+
+/* Render with the current lists: replaces the four render entries
+ *   vrt::render_image<Radiance>(w, h, image, cam, origin, gaussians, running)            rt.h:227-247
+ *   vrt::render_image<Radiance>(w, h, image, cam, origin, tiles, running, tc)            rt.h:251-310
+ *   vrt::simd_render_image<Exp,Erf>(w, h, image, cam, origin, gaussians, running)        rt.h:315-337
+ *   vrt::simd_render_image<Exp,Erf>(w, h, image, cam, origin, tiles, running, tc)        rt.h:344-404
+ * `image` receives width*height packed 0xAARRGGBB pixels (row-major); `radiance` (may be NULL) receives
+ * width*height float4 (x,y,z,w of the reference's vec4f_t colour before clamping) for parity tests.
+ * Rows outside [row_begin,row_end) are left untouched.  Host pointers; the copy back is part of the call. */
+int vrt_cuda_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance,
+                    vrt_cuda_stats *stats);
+
+/* Same with DEVICE output pointers (full-image sized buffers on the context's GPU); no copy back and no
+ * host synchronisation unless `stats` is non-NULL.  Work is enqueued on the context's stream;
+ * vrt_cuda_sync() waits for it.  Used by the multi-GPU path (bands are gathered with NCCL afterwards). */
+int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image_dev, float *radiance_dev,
+                           vrt_cuda_stats *stats);
+
+/* vrt_cuda_tile + vrt_cuda_render in one call: one iteration of the app's frame loop (main.cpp:257-297). */
+int vrt_cuda_frame_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance,
+                          vrt_cuda_stats *stats);
+
+/* Per-tile-row cost (sum over the row's cells of pixels * 5 * n^2) of the last vrt_cuda_tile(), for
+ * work-balanced row bands (include/vrt_host.h: vrt_host_row_bands).  rows_out: tiles_y (or block rows). */
+int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, uint32_t *n_rows_out, uint32_t *row_height_px_out);
+
+/* Kernel tuning knob for benchmarks (not part of the reference's surface): emitters per register block
+ * Q in {2,4,6,8} and packed f32x2 arithmetic on (1) / off (0).  Defaults are the tuned values. */
+int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
+
+int vrt_cuda_sync(vrt_cuda_ctx *ctx);
+/* The context's cudaStream_t as an integer (for ordering NCCL / torch work after a render_device). */
+uint64_t vrt_cuda_stream(vrt_cuda_ctx *ctx);
+int vrt_cuda_device(const vrt_cuda_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRT_CUDA_H */

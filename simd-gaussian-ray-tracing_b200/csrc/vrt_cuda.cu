@@ -1,0 +1,1414 @@
+// vrt_cuda.cu -- B200 (sm_100a) render path of the `vrt` Gaussian ray tracer behind include/vrt_cuda.h.
+//
+// Replaces, from scratch and warp-first rather than SIMD-first:
+//   K0  k0_prepare      per-Gaussian frame constants + the tiling projection   (src/vrt/rt.cpp:35-45)
+//   K1  k1_cull         per-cell Gaussian lists, warp ballot + popc compaction (src/vrt/rt.cpp:47-66)
+//       k1_scan/k1_order exclusive scan of the counts, cost-ordered work queue
+//   K2  k2_render       per-pixel radiance, closed-form erf transmittance      (src/vrt/rt.h:102-127, 205-223)
+//   K3  (K2 epilogue)   clamp / quantise / pack 0xAARRGGBB / vector stores      (src/vrt/rt.h:329-333, 373-377, 388-399)
+//
+// Work decomposition: one WARP owns one 8x4-pixel cell (lane = pixel) and its own Gaussian list; warps are
+// persistent and pull cells from a cost-ordered atomic queue, so there is no block-level barrier anywhere in
+// the render kernel.  See DESIGN.md for the algebra (sample-invariant terms hoisted out of the n^2 loop) and
+// the roofline.
+//
+// No CPU fallback: every entry point fails without a CUDA device.  Nothing under oracle/ is used here.
+#include "vrt_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int CELL_W = 8;          // pixels per cell (= one warp), x
+constexpr int CELL_H = 4;          // y
+constexpr int BIN_CX = 16;         // cells per coarse bin, x  (128 px)
+constexpr int BIN_CY = 32;         // cells per coarse bin, y  (128 px)
+constexpr int ROOT_SEG = 4096;     // Gaussians per root segment in the first cull level
+constexpr int K2_WARPS = 8;        // warps per render CTA
+constexpr int STAGE = 32;          // records staged per warp per step (one per lane)
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float SQRT_PI_2 = 1.2533141373155003f; // sqrt(pi/2) = 1/0.7978845608 (INV_SQRT_2_PI of src/vrt/rt.h:19)
+constexpr float REF_CULL_SIGMAS = 3.3f;           // src/vrt/rt.cpp:58-59
+
+struct FrameGeom
+{
+    // camera
+    float inv0[3], inv1[3], inv3[3]; // columns 0, 1, 3 of inverse(view) (xyz)
+    float origin[3];
+    float view[16];
+    // image
+    int W, H;
+    int tiles_x, tiles_y, tile_w, tile_h;
+    int cptx, cpty;   // cells per tile
+    int ncx, ncy;     // global cell grid
+    int nbx, nby;     // coarse bins
+    int row_begin, row_end;
+    // list semantics
+    int use_ref;      // apply the reference predicate
+    int use_bound;    // apply the per-cell k-sigma bound
+    int list_kind;    // 0: per-cell lists (index), 1: per-tile lists, 2: single list (all)
+    float bound_k;
+    float tw, th;     // 2/tiles
+    float half_w, half_h; // W/2, H/2 as float
+};
+
+__constant__ FrameGeom c_geom;
+__constant__ float c_tile_cx[1024]; // float-accumulated tile centres (src/vrt/rt.cpp:47-49)
+__constant__ float c_tile_cy[1024];
+
+// per-Gaussian frame record: 3 x float4
+//   a = (oc.x, oc.y, oc.z, (mu.w - o.w)^2)            oc = mu - origin
+//   b = (r = 1/(sqrt2 sigma), r2l = log2e/(2 sigma^2), Kl = sigma c sqrt(pi/2) log2e, sigma)
+//   c = albedo xyzw
+struct alignas(16) Rec
+{
+    float4 a, b, c;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float copysign_bits(float mag, float sgn)
+{
+    // (mag & 0x7fffffff) | (sgn & 0x80000000): one LOP3 on the ALU pipe
+    return __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | (__float_as_uint(sgn) & 0x80000000u));
+}
+
+// Abramowitz-Stegun 7.1.27 with the reference's coefficients (src/vrt/approx.cpp:90-110):
+//   erf(x) = sign(x) (1 - 1/(1 + a1|x| + a2 x^2 + a3 |x|^3 + a4 x^4)^4)
+// 4 FFMA + 2 FMUL + MUFU.RCP + FADD on the FMA/XU pipes, |x| and the sign transfer on the ALU pipe.
+constexpr float AS_A1 = 0.278393f, AS_A2 = 0.230389f, AS_A3 = 0.000972f, AS_A4 = 0.078108f;
+
+__device__ __forceinline__ float erf_as(float t)
+{
+    const float x = fabsf(t);
+    float d = fmaf(AS_A4, x, AS_A3);
+    d = fmaf(d, x, AS_A2);
+    d = fmaf(d, x, AS_A1);
+    d = fmaf(d, x, 1.f);
+    d = d * d;
+    d = d * d;
+    return copysign_bits(1.f - rcp_approx(d), t);
+}
+
+// libm-class erf on the FMA pipe: erf(|x|) = 1 - 2^(-|x| P(|x|)), P of degree 6 fitted on [0, 4]
+// (tools/fit_erf.py: max abs error 7.7e-8 in exact arithmetic, 1.7e-7 with fp32 Horner, against double
+// erf; |x| is clamped to 4 where the form returns 1 - 1.7e-8).  6 FFMA + FMUL + MUFU.EX2 + FADD.
+constexpr float EX_XMAX = 4.0f;
+constexpr float EX_C0 = 1.6279137324e+00f, EX_C1 = 9.1832863539e-01f, EX_C2 = 1.4896371499e-01f, EX_C3 = -2.9452616825e-02f,
+                EX_C4 = 2.3023453175e-03f, EX_C5 = 4.6152042132e-04f, EX_C6 = -1.0021147713e-04f;
+
+__device__ __forceinline__ float erf_exact(float t)
+{
+    const float x = fminf(fabsf(t), EX_XMAX);
+    float p = fmaf(EX_C6, x, EX_C5);
+    p = fmaf(p, x, EX_C4);
+    p = fmaf(p, x, EX_C3);
+    p = fmaf(p, x, EX_C2);
+    p = fmaf(p, x, EX_C1);
+    p = fmaf(p, x, EX_C0);
+    return copysign_bits(1.f - ex2_approx(-p * x), t);
+}
+
+template <int ERF>
+__device__ __forceinline__ float erf_variant(float t)
+{
+    return ERF == 0 ? erf_as(t) : erf_exact(t);
+}
+
+// Packed (2 x fp32) forms: Blackwell issues FFMA2 / FMUL2 / FADD2 on 64-bit register pairs, halving the
+// issue slots of the FMA-pipe part of the inner term (the loop is issue-bound in scalar form).
+template <int ERF>
+__device__ __forceinline__ float2 erf_variant2(float2 t)
+{
+    if (ERF == 0)
+    {
+        const float2 x = make_float2(fabsf(t.x), fabsf(t.y));
+        float2 d = __ffma2_rn(make_float2(AS_A4, AS_A4), x, make_float2(AS_A3, AS_A3));
+        d = __ffma2_rn(d, x, make_float2(AS_A2, AS_A2));
+        d = __ffma2_rn(d, x, make_float2(AS_A1, AS_A1));
+        d = __ffma2_rn(d, x, make_float2(1.f, 1.f));
+        d = __fmul2_rn(d, d);
+        d = __fmul2_rn(d, d);
+        const float2 rc = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+        const float2 v = __ffma2_rn(rc, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+        return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
+    }
+    else
+    {
+        const float2 x = make_float2(fminf(fabsf(t.x), EX_XMAX), fminf(fabsf(t.y), EX_XMAX));
+        float2 p = __ffma2_rn(make_float2(EX_C6, EX_C6), x, make_float2(EX_C5, EX_C5));
+        p = __ffma2_rn(p, x, make_float2(EX_C4, EX_C4));
+        p = __ffma2_rn(p, x, make_float2(EX_C3, EX_C3));
+        p = __ffma2_rn(p, x, make_float2(EX_C2, EX_C2));
+        p = __ffma2_rn(p, x, make_float2(EX_C1, EX_C1));
+        p = __ffma2_rn(p, x, make_float2(EX_C0, EX_C0));
+        const float2 q = __fmul2_rn(p, make_float2(-x.x, -x.y));
+        const float2 ex = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+        const float2 v = __ffma2_rn(ex, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+        return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: per-Gaussian frame constants
+// ------------------------------------------------------------------------------------------------
+// cull record: (mu'.x, mu'.y, 3.3 sigma', valid) of the reference's tiling projection (rt.cpp:35-45)
+__global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__restrict__ rec, float4 *__restrict__ cullrec)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *g = aos + i * 10;
+    const float ax = g[0], ay = g[1], az = g[2], aw = g[3];
+    const float mx = g[4], my = g[5], mz = g[6], mw = g[7];
+    const float sigma = g[8], mag = g[9];
+    Rec r;
+    r.a = make_float4(mx - c_geom.origin[0], my - c_geom.origin[1], mz - c_geom.origin[2], mw * mw);
+    const float rr = 1.f / (1.41421356237309504880f * sigma);
+    r.b = make_float4(rr, LOG2E / (2.f * sigma * sigma), sigma * mag * SQRT_PI_2 * LOG2E, sigma);
+    r.c = make_float4(ax, ay, az, aw);
+    rec[i] = r;
+    if (cullrec != nullptr)
+    {
+        // proj = view * (mu.xyz, 1), GLM operand order (c0 x + c1 y) + (c2 z + c3 w)
+        const float *v = c_geom.view;
+        const float px = (v[0] * mx + v[4] * my) + (v[8] * mz + v[12]);
+        const float py = (v[1] * mx + v[5] * my) + (v[9] * mz + v[13]);
+        const float pz = (v[2] * mx + v[6] * my) + (v[10] * mz + v[14]);
+        const float inv = 1.f / pz;
+        const float sg = sigma * inv;
+        const bool valid = !(pz < 1.f) && !(sg < 1e-5f);
+        cullrec[i] = make_float4(px * inv, py * inv, REF_CULL_SIGMAS * sg, valid ? 1.f : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: culling
+// ------------------------------------------------------------------------------------------------
+struct CullRect
+{
+    // outward unit normals of the four side planes of the rect's ray frustum (apex = origin)
+    float nl[3], nr[3], nb[3], nt[3];
+    int tx0, tx1, ty0, ty1; // reference tile range covered
+    bool exact_tile;        // single tile: evaluate the predicate exactly
+};
+
+__device__ __forceinline__ void cross3(const float *a, const float *b, float *r)
+{
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void orient_normalize(float *n, const float *towards, float sign)
+{
+    const float inv = rsqrtf(fmaxf(dot3(n, n), 1e-30f));
+    const float s = (dot3(n, towards) * sign >= 0.f) ? inv : -inv;
+    n[0] *= s; n[1] *= s; n[2] *= s;
+}
+
+// pixel rect [x0,x1) x [y0,y1) -> frustum planes through the extreme sample positions
+__device__ void make_rect(int x0, int x1, int y0, int y1, CullRect &rc)
+{
+    const FrameGeom &G = c_geom;
+    const float u0 = -1.f + (float)x0 / G.half_w, u1 = -1.f + (float)(x1 - 1) / G.half_w;
+    const float v0 = -1.f + (float)y0 / G.half_h, v1 = -1.f + (float)(y1 - 1) / G.half_h;
+    float Wv[3], a[3];
+    for (int i = 0; i < 3; ++i) Wv[i] = G.inv3[i] - G.origin[i];
+    // left / right planes contain U = inv1 and the ray (u * inv0 + Wv)
+    for (int i = 0; i < 3; ++i) a[i] = u0 * G.inv0[i] + Wv[i];
+    cross3(G.inv1, a, rc.nl); orient_normalize(rc.nl, G.inv0, -1.f);
+    for (int i = 0; i < 3; ++i) a[i] = u1 * G.inv0[i] + Wv[i];
+    cross3(G.inv1, a, rc.nr); orient_normalize(rc.nr, G.inv0, +1.f);
+    // bottom / top planes contain R = inv0 and the ray (v * inv1 + Wv)
+    for (int i = 0; i < 3; ++i) a[i] = v0 * G.inv1[i] + Wv[i];
+    cross3(G.inv0, a, rc.nb); orient_normalize(rc.nb, G.inv1, -1.f);
+    for (int i = 0; i < 3; ++i) a[i] = v1 * G.inv1[i] + Wv[i];
+    cross3(G.inv0, a, rc.nt); orient_normalize(rc.nt, G.inv1, +1.f);
+    rc.tx0 = x0 / G.tile_w; rc.tx1 = (x1 - 1) / G.tile_w;
+    rc.ty0 = y0 / G.tile_h; rc.ty1 = (y1 - 1) / G.tile_h;
+    rc.exact_tile = (rc.tx0 == rc.tx1) && (rc.ty0 == rc.ty1);
+}
+
+// reference predicate for one axis (src/vrt/rt.cpp:57-59): |c - mu'| <= |c| + t/2 + 3.3 sigma'
+__device__ __forceinline__ bool ref_axis(float c, float mu, float half_t, float s33) { return fabsf(c - mu) <= fabsf(c) + half_t + s33; }
+
+__device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, const float sigma, const float4 cr)
+{
+    const FrameGeom &G = c_geom;
+    if (G.use_ref)
+    {
+        if (cr.w == 0.f) return false;
+        const float hx = G.tw / 2, hy = G.th / 2;
+        if (rc.exact_tile)
+        {
+            if (!(ref_axis(c_tile_cx[rc.tx0], cr.x, hx, cr.z) && ref_axis(c_tile_cy[rc.ty0], cr.y, hy, cr.z))) return false;
+        }
+        else
+        {
+            // |c - mu| - |c| is monotone in c, so a tile range passes iff one of its end tiles does;
+            // the slack keeps the coarse level conservative against rounding of the exact test.
+            const float s = cr.z + 1e-4f;
+            const bool px = ref_axis(c_tile_cx[rc.tx0], cr.x, hx, s) || ref_axis(c_tile_cx[rc.tx1], cr.x, hx, s);
+            const bool py = ref_axis(c_tile_cy[rc.ty0], cr.y, hy, s) || ref_axis(c_tile_cy[rc.ty1], cr.y, hy, s);
+            if (!(px && py)) return false;
+        }
+    }
+    if (G.use_bound)
+    {
+        const float p[3] = {a.x, a.y, a.z};
+        // distance budget: k sigma, plus the w offset can only increase the true distance (ignored => conservative)
+        const float lim = G.bound_k * sigma + 1e-6f * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z));
+        const float dl = dot3(p, rc.nl), dr = dot3(p, rc.nr), db = dot3(p, rc.nb), dt = dot3(p, rc.nt);
+        const bool front = dl <= lim && dr <= lim && db <= lim && dt <= lim;
+        // the reference integrates along the whole line (samples with s < 0 are not guarded, rt.h:155-160),
+        // so the mirrored frustum counts too
+        const bool back = -dl <= lim && -dr <= lim && -db <= lim && -dt <= lim;
+        if (!(front || back)) return false;
+    }
+    return true;
+}
+
+// level 0: children = coarse bins, parent = root segments (identity lists); one warp per (bin, segment)
+// level 1: children = cells, parent = the bin's list; one warp per cell
+// WRITE = false: counts[child * n_seg + seg] ; WRITE = true: indices at offsets[child * n_seg + seg]
+template <bool WRITE, int LEVEL>
+__global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root,
+                                               int n_seg, const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ parent_idx,
+                                               uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, uint32_t *__restrict__ out_idx,
+                                               uint32_t n_work)
+{
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= n_work) return;
+    const FrameGeom &G = c_geom;
+    const uint32_t child = wid / n_seg, seg = wid % n_seg;
+    int x0, x1, y0, y1;
+    uint32_t begin, end;
+    if (LEVEL == 0)
+    {
+        const int bx = child % G.nbx, by = child / G.nbx;
+        // pixel rect of the bin = union of its cells' rects
+        const int cx0 = bx * BIN_CX, cx1 = min(G.ncx, cx0 + BIN_CX) - 1;
+        const int cy0 = by * BIN_CY, cy1 = min(G.ncy, cy0 + BIN_CY) - 1;
+        x0 = (cx0 / G.cptx) * G.tile_w + (cx0 % G.cptx) * CELL_W;
+        y0 = (cy0 / G.cpty) * G.tile_h + (cy0 % G.cpty) * CELL_H;
+        x1 = min((cx1 / G.cptx) * G.tile_w + min(G.tile_w, (cx1 % G.cptx + 1) * CELL_W), G.W);
+        y1 = min((cy1 / G.cpty) * G.tile_h + min(G.tile_h, (cy1 % G.cpty + 1) * CELL_H), G.H);
+        begin = seg * ROOT_SEG;
+        end = min(n_root, begin + ROOT_SEG);
+    }
+    else
+    {
+        const int cx = child % G.ncx, cy = child / G.ncx;
+        x0 = (cx / G.cptx) * G.tile_w + (cx % G.cptx) * CELL_W;
+        y0 = (cy / G.cpty) * G.tile_h + (cy % G.cpty) * CELL_H;
+        x1 = min((cx / G.cptx) * G.tile_w + min(G.tile_w, (cx % G.cptx + 1) * CELL_W), G.W);
+        y1 = min((cy / G.cpty) * G.tile_h + min(G.tile_h, (cy % G.cpty + 1) * CELL_H), G.H);
+        const uint32_t bin = (cy / BIN_CY) * G.nbx + (cx / BIN_CX);
+        begin = parent_off[bin];
+        end = parent_off[bin + 1];
+    }
+    CullRect rc;
+    make_rect(x0, x1, y0, y1, rc);
+    // cells outside the rendered row band get empty lists
+    const bool in_band = (LEVEL == 0) || (y1 > G.row_begin && y0 < G.row_end);
+
+    uint32_t base = WRITE ? offsets[wid] : 0u;
+    uint32_t count = 0;
+    if (in_band)
+    {
+        for (uint32_t k = begin; k < end; k += 32)
+        {
+            const uint32_t e = k + lane;
+            bool pass = false;
+            uint32_t gi = 0;
+            if (e < end)
+            {
+                gi = (LEVEL == 0) ? e : parent_idx[e];
+                const float4 a = rec[gi].a;
+                const float sigma = rec[gi].b.w;
+                const float4 cr = G.use_ref ? cullrec[gi] : make_float4(0.f, 0.f, 0.f, 1.f);
+                pass = cull_test(rc, a, sigma, cr);
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+            if (WRITE)
+            {
+                if (pass) out_idx[base + __popc(ballot & ((1u << lane) - 1u))] = gi;
+                base += __popc(ballot);
+            }
+            else count += __popc(ballot);
+        }
+    }
+    if (!WRITE && lane == 0) counts[wid] = count;
+}
+
+// pure REFERENCE lists (one list per reference tile), level 1 with children = tiles
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k1_cull_tiles(const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root,
+                                                     uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
+                                                     uint32_t *__restrict__ out_idx, uint32_t n_tiles)
+{
+    // one CTA per tile; ordered compaction across the CTA's 8 warps
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const FrameGeom &G = c_geom;
+    const uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const int tx = tile % G.tiles_x, ty = tile / G.tiles_x;
+    const float cx = c_tile_cx[tx], cy = c_tile_cy[ty];
+    const float hx = G.tw / 2, hy = G.th / 2;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = WRITE ? offsets[tile] : 0u;
+    __syncthreads();
+    for (uint32_t k = 0; k < n_root; k += 256)
+    {
+        const uint32_t i = k + threadIdx.x;
+        bool pass = false;
+        if (i < n_root)
+        {
+            const float4 cr = cullrec[i];
+            pass = cr.w != 0.f && ref_axis(cx, cr.x, hx, cr.z) && ref_axis(cy, cr.y, hy, cr.z);
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        if (lane == 0) s_warp[w] = __popc(ballot);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int q = 0; q < 8; ++q)
+        {
+            const uint32_t c = s_warp[q];
+            if (q < w) before += c;
+            total += c;
+        }
+        if (WRITE && pass) out_idx[s_base + before + __popc(ballot & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+    }
+    __syncthreads();
+    if (!WRITE && threadIdx.x == 0) counts[tile] = s_base;
+}
+
+// exclusive scan of n counts into n+1 offsets; single CTA of 1024 threads (n <= a few million)
+__global__ void __launch_bounds__(1024) k1_scan(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n)
+{
+    __shared__ uint32_t s_part[1024];
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t b = threadIdx.x * per, e = min(n, b + per);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += counts[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partials
+    for (int d = 1; d < 1024; d <<= 1)
+    {
+        const uint32_t v = (threadIdx.x >= (uint32_t)d) ? s_part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint32_t i = b; i < e; ++i)
+    {
+        offsets[i] = run;
+        run += counts[i];
+    }
+    if (threadIdx.x == 1023) offsets[n] = s_part[1023];
+}
+
+// statistics + cost histogram of the render cells.  list id of a cell: per-cell lists -> cell, per-tile ->
+// its tile, single -> 0.  key = min(n, 65535); the queue is filled in descending key order.
+struct TileStats
+{
+    unsigned long long entries;   // sum n over lists
+    unsigned long long max_list;
+    double terms_listed;          // sum over band pixels of 5 n^2
+    unsigned long long terms_exec; // filled by K2
+};
+
+__device__ __forceinline__ uint32_t cell_list_id(int cx, int cy)
+{
+    const FrameGeom &G = c_geom;
+    if (G.list_kind == 0) return (uint32_t)(cy * G.ncx + cx);
+    if (G.list_kind == 1) return (uint32_t)((cy / G.cpty) * G.tiles_x + (cx / G.cptx));
+    return 0u;
+}
+
+__device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int &w, int &h)
+{
+    const FrameGeom &G = c_geom;
+    const int lx = (cx % G.cptx) * CELL_W, ly = (cy % G.cpty) * CELL_H;
+    x0 = (cx / G.cptx) * G.tile_w + lx;
+    y0 = (cy / G.cpty) * G.tile_h + ly;
+    w = min(CELL_W, G.tile_w - lx);
+    h = min(CELL_H, G.tile_h - ly);
+}
+
+__global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
+                        double *__restrict__ row_cost, int cy_begin, int cy_end)
+{
+    const FrameGeom &G = c_geom;
+    const int ncells = (cy_end - cy_begin) * G.ncx;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double terms = 0.0;
+    if (i < ncells)
+    {
+        const int cx = i % G.ncx, cy = cy_begin + i / G.ncx;
+        int x0, y0, w, h;
+        cell_rect(cx, cy, x0, y0, w, h);
+        const int ya = max(y0, G.row_begin), yb = min(y0 + h, G.row_end);
+        const uint32_t id = cell_list_id(cx, cy);
+        const uint32_t n = list_off[id + 1] - list_off[id];
+        if (yb > ya)
+        {
+            terms = 5.0 * (double)n * (double)n * (double)(w * (yb - ya));
+            atomicAdd(&hist[min(n, 65535u)], 1u);
+            if (row_cost != nullptr) atomicAdd(&row_cost[cy], terms);
+        }
+    }
+    // block reduction of terms
+    for (int o = 16; o > 0; o >>= 1) terms += __shfl_xor_sync(0xffffffffu, terms, o);
+    if ((threadIdx.x & 31) == 0 && terms != 0.0) atomicAdd(&stats->terms_listed, terms);
+}
+
+__global__ void k1_list_stats(const uint32_t *__restrict__ list_off, uint32_t n_lists, TileStats *__restrict__ stats)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = 0;
+    if (i < n_lists) n = list_off[i + 1] - list_off[i];
+    uint32_t mx = n;
+    unsigned long long sum = n;
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && sum)
+    {
+        atomicAdd(&stats->entries, sum);
+        atomicMax(&stats->max_list, (unsigned long long)mx);
+    }
+}
+
+// hist (ascending key) -> start position of each key in a DESCENDING ordering; single CTA
+__global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t s_part[1024];
+    // thread t owns keys [t*64, t*64+64) ; descending order => process from the top
+    const int t = threadIdx.x;
+    uint32_t sum = 0;
+    for (int k = 0; k < 64; ++k) sum += hist[65535 - (t * 64 + k)];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1)
+    {
+        const uint32_t v = (t >= d) ? s_part[t - d] : 0u;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[t] - sum;
+    for (int k = 0; k < 64; ++k)
+    {
+        const int key = 65535 - (t * 64 + k);
+        const uint32_t c = hist[key];
+        hist[key] = run;
+        run += c;
+    }
+}
+
+__global__ void k1_order(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, int cy_begin, int cy_end)
+{
+    const FrameGeom &G = c_geom;
+    const int ncells = (cy_end - cy_begin) * G.ncx;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncells) return;
+    const int cx = i % G.ncx, cy = cy_begin + i / G.ncx;
+    int x0, y0, w, h;
+    cell_rect(cx, cy, x0, y0, w, h);
+    if (min(y0 + h, G.row_end) <= max(y0, G.row_begin)) return;
+    const uint32_t id = cell_list_id(cx, cy);
+    const uint32_t n = list_off[id + 1] - list_off[id];
+    const uint32_t pos = atomicAdd(&cursor[min(n, 65535u)], 1u);
+    queue[pos] = (uint32_t)(cy * G.ncx + cx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 + K3: render
+// ------------------------------------------------------------------------------------------------
+struct RenderArgs
+{
+    const Rec *rec;            // frame records
+    const uint32_t *list_off;  // per list: [off, off+n)
+    const uint32_t *list_idx;  // indices into rec, or nullptr when lists are contiguous ranges of rec
+    const uint32_t *queue;     // cost-ordered cell ids
+    uint32_t n_queue;
+    uint32_t *counter;         // work-queue head
+    uint32_t *image;           // W*H packed pixels (may be null)
+    float4 *radiance;          // W*H float4 (may be null)
+    unsigned long long *terms_exec;
+    float skip_thresh;         // skip an occluder / emitter for the whole warp when exp2 weight <= thresh (-1: never)
+    uint32_t quant_nearest, alpha_from_w;
+};
+
+// per-warp staging buffer: STAGE records, occluder part (a, b) and emitter part (c)
+struct WarpStage
+{
+    float4 a[STAGE];
+    float4 b[STAGE];
+    float4 c[STAGE];
+};
+
+struct PixelRay
+{
+    float nx, ny, nz;
+};
+
+// occluder quantities for this lane's ray: weight A (log2 units), mu_bar, and exp2 factor e
+__device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, const PixelRay &ray, float &mu, float &e)
+{
+    mu = fmaf(a.z, ray.nz, fmaf(a.y, ray.ny, a.x * ray.nx));
+    // squared distance from the centre to the ray, from the perpendicular component (no |oc|^2 - mu^2 cancellation)
+    const float px = fmaf(-mu, ray.nx, a.x), py = fmaf(-mu, ray.ny, a.y), pz = fmaf(-mu, ray.nz, a.z);
+    const float d2 = fmaf(pz, pz, fmaf(py, py, fmaf(px, px, a.w)));
+    e = ex2_approx(-d2 * b.y);
+}
+
+template <int ERF, int Q, bool PACK>
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_render(const RenderArgs args)
+{
+    __shared__ WarpStage s_stage[K2_WARPS];
+    const FrameGeom &G = c_geom;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStage &st = s_stage[warp];
+    const int lx = lane & (CELL_W - 1), ly = lane >> 3;
+    unsigned long long exec = 0;
+
+    for (;;)
+    {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(args.counter, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= args.n_queue) break;
+        const uint32_t cell = args.queue[qi];
+        const int cx = cell % G.ncx, cy = cell / G.ncx;
+        int x0, y0, cw, ch;
+        cell_rect(cx, cy, x0, y0, cw, ch);
+        const int px = x0 + min(lx, cw - 1), py = y0 + min(ly, ch - 1);
+        const bool live = lx < cw && ly < ch && py >= G.row_begin && py < G.row_end;
+        const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
+
+        // ray through the pixel: plane = inverse(view) (u, v, 0, 1) (src/vrt/camera.cpp:60-70); dir = normalize(plane - origin)
+        PixelRay ray;
+        {
+            const float u = -1.f + (float)px / G.half_w, v = -1.f + (float)py / G.half_h;
+            const float dx = (G.inv0[0] * u + G.inv1[0] * v) + G.inv3[0] - G.origin[0];
+            const float dy = (G.inv0[1] * u + G.inv1[1] * v) + G.inv3[1] - G.origin[1];
+            const float dz = (G.inv0[2] * u + G.inv1[2] * v) + G.inv3[2] - G.origin[2];
+            const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+            ray.nx = dx * inv; ray.ny = dy * inv; ray.nz = dz * inv;
+        }
+
+        const uint32_t lid = cell_list_id(cx, cy);
+        const uint32_t off = args.list_off[lid];
+        const uint32_t n = args.list_off[lid + 1] - off;
+
+        auto load_rec = [&](uint32_t k) -> const Rec * {
+            const uint32_t gi = args.list_idx ? args.list_idx[off + k] : off + k;
+            return args.rec + gi;
+        };
+
+        // ---- pass A: C = sum_j A_j erf(-m_j)   (the sample-independent half of every term) ----
+        float C = 0.f;
+        for (uint32_t j0 = 0; j0 < n; j0 += STAGE)
+        {
+            const uint32_t cnt = min((uint32_t)STAGE, n - j0);
+            __syncwarp();
+            if ((uint32_t)lane < cnt)
+            {
+                const Rec *r = load_rec(j0 + lane);
+                st.a[lane] = r->a;
+                st.b[lane] = r->b;
+            }
+            __syncwarp();
+            for (uint32_t j = 0; j < cnt; ++j)
+            {
+                const float4 a = st.a[j], b = st.b[j];
+                float mu, e;
+                occluder_setup(a, b, ray, mu, e);
+                C = fmaf(b.z * e, erf_variant<ERF>(-mu * b.x), C);
+            }
+        }
+
+        // ---- pass B: emitters in blocks of Q, all occluders per block ----
+        float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
+        for (uint32_t q0 = 0; q0 < n; q0 += Q)
+        {
+            // emitter block
+            float s[Q][5], acc[Q][5], wgt[Q];
+            float4 alb[Q];
+            float s0 = 0.f;
+            bool any_emit = false;
+#pragma unroll
+            for (int e = 0; e < Q; ++e)
+            {
+                const bool real = q0 + e < n;
+                const Rec *r = load_rec(real ? q0 + e : q0);
+                const float4 a = r->a, b = r->b;
+                alb[e] = r->c;
+                float mu, ee;
+                occluder_setup(a, b, ray, mu, ee);
+                if (e == 0) s0 = __shfl_sync(0xffffffffu, mu, 0); // one depth shift per warp keeps s r - m small
+                // emission weight sigma c_bar = Kl e / (sqrt(pi/2) log2e)
+                wgt[e] = real ? b.z * ee * (1.f / (SQRT_PI_2 * LOG2E)) : 0.f;
+                any_emit |= real && (ee > args.skip_thresh);
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                {
+                    s[e][k] = (mu - s0) + (float)(k - 4) * b.w;
+                    acc[e][k] = 0.f;
+                }
+            }
+            if (!__any_sync(0xffffffffu, any_emit)) continue; // no lane sees any of these emitters
+            const uint32_t n_real = min((uint32_t)Q, n - q0);
+
+            for (uint32_t j0 = 0; j0 < n; j0 += STAGE)
+            {
+                const uint32_t cnt = min((uint32_t)STAGE, n - j0);
+                if (n > STAGE || q0 == 0)
+                {
+                    // (re)stage; lists that fit one stage stay resident from pass A
+                    __syncwarp();
+                    if ((uint32_t)lane < cnt)
+                    {
+                        const Rec *r = load_rec(j0 + lane);
+                        st.a[lane] = r->a;
+                        st.b[lane] = r->b;
+                    }
+                    __syncwarp();
+                }
+                for (uint32_t j = 0; j < cnt; ++j)
+                {
+                    const float4 a = st.a[j], b = st.b[j];
+                    float mu, e;
+                    occluder_setup(a, b, ray, mu, e);
+                    if (!__any_sync(0xffffffffu, e > args.skip_thresh)) continue; // warp-uniform skip
+                    const float A = b.z * e;
+                    const float r = b.x;
+                    const float nm = -(mu - s0) * r;
+                    exec += n_real;
+                    if (PACK)
+                    {
+                        const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(A, A);
+#pragma unroll
+                        for (int e2 = 0; e2 < Q / 2; ++e2)
+#pragma unroll
+                            for (int k = 0; k < 5; ++k)
+                            {
+                                const float2 t = __ffma2_rn(make_float2(s[2 * e2][k], s[2 * e2 + 1][k]), rr, mm);
+                                const float2 ev = erf_variant2<ERF>(t);
+                                const float2 ac = __ffma2_rn(AA, ev, make_float2(acc[2 * e2][k], acc[2 * e2 + 1][k]));
+                                acc[2 * e2][k] = ac.x;
+                                acc[2 * e2 + 1][k] = ac.y;
+                            }
+                        if (Q & 1)
+                        {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) acc[Q - 1][k] = fmaf(A, erf_variant<ERF>(fmaf(s[Q - 1][k], r, nm)), acc[Q - 1][k]);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int e = 0; e < Q; ++e)
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) acc[e][k] = fmaf(A, erf_variant<ERF>(fmaf(s[e][k], r, nm)), acc[e][k]);
+                    }
+                }
+            }
+            // T(s) = 2^(C - acc); pdf at the samples = c_bar e^{-k^2/2}, k = -4..0 (src/vrt/rt.h:153-161)
+#pragma unroll
+            for (int e = 0; e < Q; ++e)
+            {
+                float inner = 3.3546262790251185e-4f * ex2_approx(C - acc[e][0]);
+                inner = fmaf(1.1108996538242306e-2f, ex2_approx(C - acc[e][1]), inner);
+                inner = fmaf(1.3533528323661270e-1f, ex2_approx(C - acc[e][2]), inner);
+                inner = fmaf(6.0653065971263342e-1f, ex2_approx(C - acc[e][3]), inner);
+                inner += ex2_approx(C - acc[e][4]);
+                inner *= wgt[e];
+                Lr = fmaf(alb[e].x, inner, Lr);
+                Lg = fmaf(alb[e].y, inner, Lg);
+                Lb = fmaf(alb[e].z, inner, Lb);
+                La = fmaf(alb[e].w, inner, La);
+            }
+        }
+
+        // ---- K3: framebuffer ----
+        if (live)
+        {
+            const size_t pi = (size_t)py * G.W + px;
+            if (args.radiance) args.radiance[pi] = make_float4(Lr, Lg, Lb, La);
+            if (args.image)
+            {
+                const float r255 = fminf(Lr, 1.f) * 255.f, g255 = fminf(Lg, 1.f) * 255.f, b255 = fminf(Lb, 1.f) * 255.f;
+                uint32_t R, Gc, B, A = 0xFFu;
+                if (args.quant_nearest)
+                {
+                    R = (uint32_t)__float2int_rn(r255); Gc = (uint32_t)__float2int_rn(g255); B = (uint32_t)__float2int_rn(b255);
+                    if (args.alpha_from_w) A = (uint32_t)__float2int_rn(fminf(La, 1.f) * 255.f);
+                }
+                else
+                {
+                    R = (uint32_t)r255; Gc = (uint32_t)g255; B = (uint32_t)b255;
+                    if (args.alpha_from_w) A = (uint32_t)(fminf(La, 1.f) * 255.f);
+                }
+                args.image[pi] = (A << 24) | (R << 16) | (Gc << 8) | B;
+            }
+        }
+        if (lane == 0 && exec)
+        {
+            atomicAdd(args.terms_exec, exec * 5ull * n_live);
+        }
+        exec = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DevBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+std::string g_create_error;
+} // namespace
+
+struct vrt_cuda_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    int sm_count = 148;
+
+    uint64_t n_gauss = 0;
+    DevBuf aos;        // scene, n x 10 floats
+    DevBuf rec;        // frame records
+    DevBuf cullrec;    // reference tiling projection
+    DevBuf counts, offsets, idx;          // level 0 (bins)
+    DevBuf ccounts, coffsets, cidx;       // level 1 (cells / tiles)
+    DevBuf hist, queue, stats, counter, rowcost;
+    DevBuf out_image, out_rad;
+    DevBuf tile_aos; // host-supplied tile lists (concatenated)
+    DevBuf tile_off;
+
+    // state of the last tile()
+    bool have_lists = false;
+    bool lists_from_host = false;
+    FrameGeom geom{};
+    uint32_t n_lists = 0;
+    uint64_t n_entries = 0;
+    uint32_t n_queue = 0;
+    int cy_begin = 0, cy_end = 0;
+    uint32_t launches = 0;
+    float ms_tile = 0.f;
+    // tuning
+    int tune_q = 4;
+    int tune_pack = 1;
+};
+
+namespace
+{
+int fail(vrt_cuda_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                                        \
+    do                                                                                                                  \
+    {                                                                                                                   \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess) return fail(ctx, VRT_CUDA_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int reserve(vrt_cuda_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(ctx, VRT_CUDA_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    b.cap = want;
+    return 0;
+}
+
+void inverse4(const float *m, float *r)
+{
+    // adjugate / determinant, column-major
+    const float a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
+    const float a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
+    const float b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10;
+    const float b03 = a01 * a12 - a02 * a11, b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12;
+    const float b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30, b08 = a20 * a33 - a23 * a30;
+    const float b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
+    const float id = 1.f / (b00 * b11 - b01 * b10 + b02 * b09 + b03 * b08 - b04 * b07 + b05 * b06);
+    r[0] = (a11 * b11 - a12 * b10 + a13 * b09) * id;  r[1] = (a02 * b10 - a01 * b11 - a03 * b09) * id;
+    r[2] = (a31 * b05 - a32 * b04 + a33 * b03) * id;  r[3] = (a22 * b04 - a21 * b05 - a23 * b03) * id;
+    r[4] = (a12 * b08 - a10 * b11 - a13 * b07) * id;  r[5] = (a00 * b11 - a02 * b08 + a03 * b07) * id;
+    r[6] = (a32 * b02 - a30 * b05 - a33 * b01) * id;  r[7] = (a20 * b05 - a22 * b02 + a23 * b01) * id;
+    r[8] = (a10 * b10 - a11 * b08 + a13 * b06) * id;  r[9] = (a01 * b08 - a00 * b10 - a03 * b06) * id;
+    r[10] = (a30 * b04 - a31 * b02 + a33 * b00) * id; r[11] = (a21 * b02 - a20 * b04 - a23 * b00) * id;
+    r[12] = (a11 * b07 - a10 * b09 - a12 * b06) * id; r[13] = (a00 * b09 - a01 * b07 + a02 * b06) * id;
+    r[14] = (a31 * b01 - a30 * b03 - a32 * b00) * id; r[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
+}
+
+// Validates the frame and fills the geometry; list_kind_override >= 0 forces the list kind (host tile lists).
+int make_geom(vrt_cuda_ctx *ctx, const vrt_cuda_frame *f, int list_kind_override, FrameGeom &G, std::vector<float> &cxs, std::vector<float> &cys)
+{
+    if (!f) return fail(ctx, VRT_CUDA_E_INVALID, "frame is NULL");
+    if (f->width == 0 || f->height == 0 || f->width > 65536 || f->height > 65536) return fail(ctx, VRT_CUDA_E_INVALID, "bad image size %ux%u", f->width, f->height);
+    if (f->origin[3] != 0.f) return fail(ctx, VRT_CUDA_E_INVALID, "origin.w must be 0 (it is in every reference call site, main.cpp:248,253)");
+    std::memset(&G, 0, sizeof(G));
+    const uint32_t lm = f->flags & VRT_CUDA_LIST_MASK;
+    const bool tiled = (list_kind_override == 1) || lm == VRT_CUDA_LIST_REFERENCE || lm == VRT_CUDA_LIST_REFERENCE_BOUND;
+    G.W = (int)f->width;
+    G.H = (int)f->height;
+    G.tiles_x = tiled ? (int)f->tiles_x : 1;
+    G.tiles_y = tiled ? (int)f->tiles_y : 1;
+    if (tiled)
+    {
+        if (f->tiles_x == 0 || f->tiles_y == 0 || f->tiles_x > 1024 || f->tiles_y > 1024) return fail(ctx, VRT_CUDA_E_INVALID, "tiles per axis must be in 1..1024");
+        if (f->width % f->tiles_x || f->height % f->tiles_y)
+            return fail(ctx, VRT_CUDA_E_INVALID, "image %ux%u is not divisible into %ux%u tiles (the reference truncates tile_width, rt.h:254)", f->width, f->height, f->tiles_x, f->tiles_y);
+    }
+    G.tile_w = G.W / G.tiles_x;
+    G.tile_h = G.H / G.tiles_y;
+    G.cptx = (G.tile_w + CELL_W - 1) / CELL_W;
+    G.cpty = (G.tile_h + CELL_H - 1) / CELL_H;
+    G.ncx = G.tiles_x * G.cptx;
+    G.ncy = G.tiles_y * G.cpty;
+    G.nbx = (G.ncx + BIN_CX - 1) / BIN_CX;
+    G.nby = (G.ncy + BIN_CY - 1) / BIN_CY;
+    G.row_begin = (int)f->row_begin;
+    G.row_end = (int)f->row_end;
+    if (f->row_begin == 0 && f->row_end == 0) G.row_end = G.H;
+    if (G.row_begin < 0 || G.row_end > G.H || G.row_begin >= G.row_end) return fail(ctx, VRT_CUDA_E_INVALID, "bad row band [%u,%u)", f->row_begin, f->row_end);
+    G.use_ref = (lm == VRT_CUDA_LIST_REFERENCE || lm == VRT_CUDA_LIST_REFERENCE_BOUND) ? 1 : 0;
+    G.use_bound = (lm == VRT_CUDA_LIST_REFERENCE_BOUND || lm == VRT_CUDA_LIST_BOUND) ? 1 : 0;
+    G.list_kind = G.use_bound ? 0 : (G.use_ref ? 1 : 2);
+    if (list_kind_override >= 0)
+    {
+        G.list_kind = list_kind_override;
+        G.use_ref = G.use_bound = 0;
+    }
+    G.bound_k = f->bound_sigmas > 0.f ? f->bound_sigmas : 6.0f;
+    G.tw = 2.f / (float)G.tiles_x;
+    G.th = 2.f / (float)G.tiles_y;
+    G.half_w = (float)G.W / 2.f;
+    G.half_h = (float)G.H / 2.f;
+    std::memcpy(G.view, f->view, sizeof(G.view));
+    float inv[16];
+    inverse4(f->view, inv);
+    for (int i = 0; i < 3; ++i)
+    {
+        G.inv0[i] = inv[i];
+        G.inv1[i] = inv[4 + i];
+        G.inv3[i] = inv[12 + i];
+        G.origin[i] = f->origin[i];
+        if (!std::isfinite(inv[i]) || !std::isfinite(inv[4 + i]) || !std::isfinite(inv[12 + i])) return fail(ctx, VRT_CUDA_E_INVALID, "view matrix is singular");
+    }
+    // tile centres by the reference's float accumulation (src/vrt/rt.cpp:47-49)
+    cxs.clear();
+    cys.clear();
+    for (float x = -1.f + G.tw / 2; x < 1.f; x += G.tw) cxs.push_back(x);
+    for (float y = -1.f + G.th / 2; y < 1.f; y += G.th) cys.push_back(y);
+    if (G.use_ref && ((int)cxs.size() != G.tiles_x || (int)cys.size() != G.tiles_y))
+        return fail(ctx, VRT_CUDA_E_INVALID, "tile count %dx%d is not reproduced by the reference's float accumulation (%zu x %zu centres)", G.tiles_x, G.tiles_y, cxs.size(), cys.size());
+    cxs.resize(1024, 0.f);
+    cys.resize(1024, 0.f);
+    return 0;
+}
+
+int upload_geom(vrt_cuda_ctx *ctx, const FrameGeom &G, const std::vector<float> &cxs, const std::vector<float> &cys)
+{
+    CU(cudaMemcpyToSymbolAsync(c_geom, &G, sizeof(G), 0, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyToSymbolAsync(c_tile_cx, cxs.data(), sizeof(float) * 1024, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyToSymbolAsync(c_tile_cy, cys.data(), sizeof(float) * 1024, 0, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// cost ordering of the band's cells + listed-term statistics
+int build_queue(vrt_cuda_ctx *ctx)
+{
+    const FrameGeom &G = ctx->geom;
+    // cell rows intersecting the band
+    int cyb = G.ncy, cye = 0;
+    for (int cy = 0; cy < G.ncy; ++cy)
+    {
+        const int y0 = (cy / G.cpty) * G.tile_h + (cy % G.cpty) * CELL_H;
+        const int h = std::min(CELL_H, G.tile_h - (cy % G.cpty) * CELL_H);
+        if (y0 + h > G.row_begin && y0 < G.row_end)
+        {
+            cyb = std::min(cyb, cy);
+            cye = std::max(cye, cy + 1);
+        }
+    }
+    ctx->cy_begin = cyb;
+    ctx->cy_end = cye;
+    const int ncells = (cye - cyb) * G.ncx;
+    if (int rc = reserve(ctx, ctx->hist, sizeof(uint32_t) * 65536)) return rc;
+    if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max(ncells, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->stats, sizeof(TileStats))) return rc;
+    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
+    if (int rc = reserve(ctx, ctx->rowcost, sizeof(double) * (size_t)G.ncy)) return rc;
+    CU(cudaMemsetAsync(ctx->hist.p, 0, sizeof(uint32_t) * 65536, ctx->stream));
+    CU(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TileStats), ctx->stream));
+    CU(cudaMemsetAsync(ctx->rowcost.p, 0, sizeof(double) * (size_t)G.ncy, ctx->stream));
+    const uint32_t *loff = (const uint32_t *)ctx->coffsets.p;
+    const int tb = 256, gb = (ncells + tb - 1) / tb;
+    k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(loff, ctx->n_lists, (TileStats *)ctx->stats.p);
+    k1_hist<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
+    k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p);
+    k1_order<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, cyb, cye);
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    // number of queued cells = cells with at least one band pixel
+    uint32_t nq = 0;
+    for (int cy = cyb; cy < cye; ++cy)
+    {
+        const int y0 = (cy / G.cpty) * G.tile_h + (cy % G.cpty) * CELL_H;
+        const int h = std::min(CELL_H, G.tile_h - (cy % G.cpty) * CELL_H);
+        if (std::min(y0 + h, G.row_end) > std::max(y0, G.row_begin)) nq += (uint32_t)G.ncx;
+    }
+    ctx->n_queue = nq;
+    return 0;
+}
+
+template <int ERF, int Q, bool PACK>
+void launch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
+{
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK>, K2_WARPS * 32, 0);
+    if (per_sm < 1) per_sm = 1;
+    const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
+    const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
+    k2_render<ERF, Q, PACK><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+}
+
+template <int ERF>
+int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
+{
+    const int q = ctx->tune_q;
+    const bool p = ctx->tune_pack != 0;
+    switch (q)
+    {
+    case 2: p ? launch_k2<ERF, 2, true>(ctx, a) : launch_k2<ERF, 2, false>(ctx, a); break;
+    case 4: p ? launch_k2<ERF, 4, true>(ctx, a) : launch_k2<ERF, 4, false>(ctx, a); break;
+    case 6: p ? launch_k2<ERF, 6, true>(ctx, a) : launch_k2<ERF, 6, false>(ctx, a); break;
+    case 8: p ? launch_k2<ERF, 8, true>(ctx, a) : launch_k2<ERF, 8, false>(ctx, a); break;
+    default: return fail(ctx, VRT_CUDA_E_INVALID, "unsupported emitter block %d", q);
+    }
+    return 0;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C"
+{
+int vrt_cuda_abi_version(void) { return VRT_CUDA_ABI_VERSION; }
+
+int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
+{
+    vrt_cuda_ctx *ctx = nullptr;
+    if (!ctx_out) return fail(ctx, VRT_CUDA_E_INVALID, "ctx_out is NULL");
+    *ctx_out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(ctx, VRT_CUDA_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(ctx, VRT_CUDA_E_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    CU(cudaSetDevice(device));
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ctx, VRT_CUDA_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    vrt_cuda_ctx *c = new vrt_cuda_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    ctx = c;
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e2 == cudaSuccess; ++i) e2 = cudaEventCreate(&c->ev[i]);
+    if (e2 != cudaSuccess)
+    {
+        g_create_error = std::string("stream/event creation failed: ") + cudaGetErrorString(e2);
+        delete c;
+        return VRT_CUDA_E_CUDA;
+    }
+    *ctx_out = c;
+    return 0;
+}
+
+void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->counts, &ctx->offsets, &ctx->idx, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
+                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *vrt_cuda_last_error(const vrt_cuda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int vrt_cuda_device(const vrt_cuda_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t vrt_cuda_stream(vrt_cuda_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+int vrt_cuda_sync(vrt_cuda_ctx *ctx)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int set_gaussians_impl(vrt_cuda_ctx *ctx, const float *aos, uint64_t n, cudaMemcpyKind kind)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (n && !aos) return fail(ctx, VRT_CUDA_E_INVALID, "aos is NULL");
+    if (n > 0xFFFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "too many Gaussians");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = reserve(ctx, ctx->aos, std::max<size_t>(n, 1) * 40)) return rc;
+    if (n) CU(cudaMemcpyAsync(ctx->aos.p, aos, n * 40, kind, ctx->stream));
+    ctx->n_gauss = n;
+    ctx->have_lists = false;
+    return 0;
+}
+
+int vrt_cuda_set_gaussians(vrt_cuda_ctx *ctx, const float *aos, uint64_t n) { return set_gaussians_impl(ctx, aos, n, cudaMemcpyHostToDevice); }
+int vrt_cuda_set_gaussians_device(vrt_cuda_ctx *ctx, const float *aos_dev, uint64_t n) { return set_gaussians_impl(ctx, aos_dev, n, cudaMemcpyDeviceToDevice); }
+
+// Internal tuning knob (emitter block size Q in {2,4,6,8}, packed f32x2 math on/off); used by the benchmarks.
+int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int q, int pack)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (q != 2 && q != 4 && q != 6 && q != 8) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 2, 4, 6 or 8");
+    ctx->tune_q = q;
+    ctx->tune_pack = pack ? 1 : 0;
+    return 0;
+}
+
+int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    FrameGeom G;
+    std::vector<float> cxs, cys;
+    if (int rc = make_geom(ctx, frame, -1, G, cxs, cys)) return rc;
+    ctx->have_lists = false;
+    ctx->lists_from_host = false;
+    ctx->geom = G;
+    ctx->launches = 0;
+    const uint64_t N = ctx->n_gauss;
+    if (int rc = upload_geom(ctx, G, cxs, cys)) return rc;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+
+    if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(N, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->cullrec, sizeof(float4) * std::max<uint64_t>(N, 1))) return rc;
+    if (N)
+    {
+        k0_prepare<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->aos.p, N, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p);
+        ctx->launches++;
+    }
+
+    if (G.list_kind == 2)
+    {
+        // single list: all Gaussians, contiguous
+        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * 2)) return rc;
+        const uint32_t off[2] = {0u, (uint32_t)N};
+        CU(cudaMemcpyAsync(ctx->coffsets.p, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); // off[] is on the stack
+        ctx->n_lists = 1;
+        ctx->n_entries = N;
+    }
+    else if (G.list_kind == 1)
+    {
+        const uint32_t nt = (uint32_t)(G.tiles_x * G.tiles_y);
+        if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * nt)) return rc;
+        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (nt + 1))) return rc;
+        k1_cull_tiles<false><<<nt, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, (uint32_t *)ctx->ccounts.p, nullptr, nullptr, nt);
+        k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, nt);
+        uint32_t total = 0;
+        CU(cudaMemcpyAsync(&total, (const uint32_t *)ctx->coffsets.p + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
+        k1_cull_tiles<true><<<nt, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nullptr, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, nt);
+        ctx->launches += 3;
+        ctx->n_lists = nt;
+        ctx->n_entries = total;
+    }
+    else
+    {
+        // level 0: bins x root segments
+        const uint32_t nbins = (uint32_t)(G.nbx * G.nby);
+        const int nseg = (int)std::max<uint64_t>(1, (N + ROOT_SEG - 1) / ROOT_SEG);
+        const uint64_t work0 = (uint64_t)nbins * nseg;
+        if (work0 > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "scene x image too large for the binning level");
+        if (int rc = reserve(ctx, ctx->counts, sizeof(uint32_t) * work0)) return rc;
+        if (int rc = reserve(ctx, ctx->offsets, sizeof(uint32_t) * (work0 + 1))) return rc;
+        const unsigned g0 = (unsigned)((work0 * 32 + 255) / 256);
+        k1_cull<false, 0><<<g0, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nseg, nullptr, nullptr,
+                                                      (uint32_t *)ctx->counts.p, nullptr, nullptr, (uint32_t)work0);
+        k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->counts.p, (uint32_t *)ctx->offsets.p, (uint32_t)work0);
+        uint32_t total0 = 0;
+        CU(cudaMemcpyAsync(&total0, (const uint32_t *)ctx->offsets.p + work0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (int rc = reserve(ctx, ctx->idx, sizeof(uint32_t) * std::max<uint32_t>(total0, 1))) return rc;
+        k1_cull<true, 0><<<g0, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nseg, nullptr, nullptr, nullptr,
+                                                     (const uint32_t *)ctx->offsets.p, (uint32_t *)ctx->idx.p, (uint32_t)work0);
+        // bin b owns [offsets[b*nseg], offsets[(b+1)*nseg]) : compact the per-bin offsets into counts (reuse as parent_off)
+        // level 1 reads parent_off[bin] = offsets[bin*nseg]; build that strided view with a tiny gather on the host side of the
+        // stream: a 1-thread-per-bin copy kernel is overkill, cudaMemcpy2DAsync does it.
+        if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * ((size_t)G.ncx * G.ncy + nbins + 2))) return rc;
+        uint32_t *bin_off = (uint32_t *)ctx->ccounts.p + (size_t)G.ncx * G.ncy; // nbins + 1 entries after the cell counts
+        CU(cudaMemcpy2DAsync(bin_off, sizeof(uint32_t), ctx->offsets.p, sizeof(uint32_t) * nseg, sizeof(uint32_t), nbins, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(bin_off + nbins, (const uint32_t *)ctx->offsets.p + work0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        // level 1: cells
+        const uint32_t ncells = (uint32_t)(G.ncx * G.ncy);
+        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * ((size_t)ncells + 1))) return rc;
+        const unsigned g1 = (unsigned)(((uint64_t)ncells * 32 + 255) / 256);
+        k1_cull<false, 1><<<g1, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, 1, bin_off, (const uint32_t *)ctx->idx.p,
+                                                      (uint32_t *)ctx->ccounts.p, nullptr, nullptr, ncells);
+        k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, ncells);
+        uint32_t total1 = 0;
+        CU(cudaMemcpyAsync(&total1, (const uint32_t *)ctx->coffsets.p + ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(total1, 1))) return rc;
+        k1_cull<true, 1><<<g1, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, 1, bin_off, (const uint32_t *)ctx->idx.p, nullptr,
+                                                     (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ncells);
+        ctx->launches += 6;
+        ctx->n_lists = ncells;
+        ctx->n_entries = total1;
+    }
+    CU(cudaGetLastError());
+    if (int rc = build_queue(ctx)) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
+    ctx->have_lists = true;
+    return 0;
+}
+
+int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, const float *aos_concat, const uint64_t *offsets, uint64_t n_tiles)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (!offsets) return fail(ctx, VRT_CUDA_E_INVALID, "offsets is NULL");
+    FrameGeom G;
+    std::vector<float> cxs, cys;
+    if (int rc = make_geom(ctx, frame, 1, G, cxs, cys)) return rc;
+    if (n_tiles != (uint64_t)G.tiles_x * G.tiles_y) return fail(ctx, VRT_CUDA_E_INVALID, "n_tiles %llu != tiles_x*tiles_y %d", (unsigned long long)n_tiles, G.tiles_x * G.tiles_y);
+    const uint64_t total = offsets[n_tiles];
+    if (total > 0xFFFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "tile lists too long");
+    if (total && !aos_concat) return fail(ctx, VRT_CUDA_E_INVALID, "aos_concat is NULL");
+    std::vector<uint32_t> off32(n_tiles + 1);
+    for (uint64_t t = 0; t <= n_tiles; ++t)
+    {
+        if (t && offsets[t] < offsets[t - 1]) return fail(ctx, VRT_CUDA_E_INVALID, "offsets must be non-decreasing");
+        off32[t] = (uint32_t)offsets[t];
+    }
+    ctx->have_lists = false;
+    ctx->geom = G;
+    ctx->launches = 0;
+    if (int rc = upload_geom(ctx, G, cxs, cys)) return rc;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (int rc = reserve(ctx, ctx->tile_aos, std::max<uint64_t>(total, 1) * 40)) return rc;
+    if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(total, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (n_tiles + 1))) return rc;
+    if (total) CU(cudaMemcpyAsync(ctx->tile_aos.p, aos_concat, total * 40, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->coffsets.p, off32.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (total)
+    {
+        k0_prepare<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->tile_aos.p, total, (Rec *)ctx->rec.p, nullptr);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    ctx->n_lists = (uint32_t)n_tiles;
+    ctx->n_entries = total;
+    ctx->lists_from_host = true;
+    if (int rc = build_queue(ctx)) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // off32 lives on this stack frame
+    CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
+    ctx->have_lists = true;
+    return 0;
+}
+
+int vrt_cuda_get_lists(vrt_cuda_ctx *ctx, uint32_t *counts_out, uint64_t counts_cap, uint32_t *idx_out, uint64_t idx_cap, uint64_t *n_cells_out, uint64_t *n_entries_out)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!ctx->have_lists) return fail(ctx, VRT_CUDA_E_STATE, "no lists: call vrt_cuda_tile first");
+    CU(cudaSetDevice(ctx->device));
+    if (n_cells_out) *n_cells_out = ctx->n_lists;
+    if (n_entries_out) *n_entries_out = ctx->n_entries;
+    if (counts_out)
+    {
+        if (counts_cap < ctx->n_lists) return fail(ctx, VRT_CUDA_E_INVALID, "counts_cap too small");
+        std::vector<uint32_t> off(ctx->n_lists + 1);
+        CU(cudaMemcpyAsync(off.data(), ctx->coffsets.p, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t i = 0; i < ctx->n_lists; ++i) counts_out[i] = off[i + 1] - off[i];
+    }
+    if (idx_out)
+    {
+        if (idx_cap < ctx->n_entries) return fail(ctx, VRT_CUDA_E_INVALID, "idx_cap too small");
+        if (ctx->geom.list_kind == 2 || ctx->lists_from_host)
+        {
+            for (uint64_t i = 0; i < ctx->n_entries; ++i) idx_out[i] = (uint32_t)i;
+        }
+        else if (ctx->n_entries)
+        {
+            CU(cudaMemcpyAsync(idx_out, ctx->cidx.p, sizeof(uint32_t) * ctx->n_entries, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return 0;
+}
+
+int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, uint32_t *n_rows_out, uint32_t *row_height_px_out)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!ctx->have_lists) return fail(ctx, VRT_CUDA_E_STATE, "no lists: call vrt_cuda_tile first");
+    CU(cudaSetDevice(ctx->device));
+    const FrameGeom &G = ctx->geom;
+    if (G.tile_h % CELL_H) return fail(ctx, VRT_CUDA_E_INVALID, "row costs need tile_h %% %d == 0", CELL_H);
+    if (n_rows_out) *n_rows_out = (uint32_t)G.ncy;
+    if (row_height_px_out) *row_height_px_out = CELL_H;
+    if (rows_out)
+    {
+        if (rows_cap < (uint32_t)G.ncy) return fail(ctx, VRT_CUDA_E_INVALID, "rows_cap too small");
+        CU(cudaMemcpyAsync(rows_out, ctx->rowcost.p, sizeof(double) * G.ncy, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image_dev, float *radiance_dev, vrt_cuda_stats *stats)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!ctx->have_lists) return fail(ctx, VRT_CUDA_E_STATE, "no lists: call vrt_cuda_tile or vrt_cuda_set_tile_lists first");
+    if (!frame) return fail(ctx, VRT_CUDA_E_INVALID, "frame is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const FrameGeom &G = ctx->geom;
+    if ((int)frame->width != G.W || (int)frame->height != G.H) return fail(ctx, VRT_CUDA_E_INVALID, "frame size differs from the tiled frame");
+    if (std::memcmp(frame->view, G.view, sizeof(G.view)) != 0 || std::memcmp(frame->origin, G.origin, sizeof(float) * 3) != 0)
+        return fail(ctx, VRT_CUDA_E_STATE, "camera changed since vrt_cuda_tile: lists are per frame");
+    {
+        const int rb = (frame->row_begin == 0 && frame->row_end == 0) ? 0 : (int)frame->row_begin;
+        const int re = (frame->row_begin == 0 && frame->row_end == 0) ? G.H : (int)frame->row_end;
+        if (rb != G.row_begin || re != G.row_end) return fail(ctx, VRT_CUDA_E_STATE, "row band differs from the tiled frame");
+    }
+    RenderArgs a{};
+    a.rec = (const Rec *)ctx->rec.p;
+    a.list_off = (const uint32_t *)ctx->coffsets.p;
+    a.list_idx = (G.list_kind == 2 || ctx->lists_from_host) ? nullptr : (const uint32_t *)ctx->cidx.p;
+    a.queue = (const uint32_t *)ctx->queue.p;
+    a.n_queue = ctx->n_queue;
+    a.counter = (uint32_t *)ctx->counter.p;
+    a.image = image_dev;
+    a.radiance = (float4 *)radiance_dev;
+    a.terms_exec = &((TileStats *)ctx->stats.p)->terms_exec;
+    const bool bounded = G.use_bound != 0;
+    a.skip_thresh = (frame->flags & VRT_CUDA_NO_SKIP) ? -1.f : (bounded ? std::exp2(-0.5f * G.bound_k * G.bound_k * LOG2E) : 0.f);
+    a.quant_nearest = (frame->flags & VRT_CUDA_QUANT_NEAREST) ? 1u : 0u;
+    a.alpha_from_w = (frame->flags & VRT_CUDA_ALPHA_FROM_W) ? 1u : 0u;
+    CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));
+    CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_exec, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    int rc = ((frame->flags & VRT_CUDA_ERF_MASK) == VRT_CUDA_ERF_EXACT) ? dispatch_k2<1>(ctx, a) : dispatch_k2<0>(ctx, a);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (stats)
+    {
+        TileStats ts;
+        CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->n_gaussians = ctx->n_gauss;
+        stats->n_cells = ctx->n_lists;
+        stats->list_entries = ts.entries;
+        stats->max_list = (uint32_t)ts.max_list;
+        stats->n_launches = ctx->launches + 1;
+        stats->terms_listed = ts.terms_listed;
+        stats->terms_executed = (double)ts.terms_exec;
+        stats->ms_tile = ctx->ms_tile;
+        CU(cudaEventElapsedTime(&stats->ms_render, ctx->ev[2], ctx->ev[3]));
+        stats->ms_total = stats->ms_tile + stats->ms_render;
+    }
+    return 0;
+}
+
+int vrt_cuda_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!frame) return fail(ctx, VRT_CUDA_E_INVALID, "frame is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)frame->width * frame->height;
+    if (image)
+        if (int rc = reserve(ctx, ctx->out_image, npix * sizeof(uint32_t))) return rc;
+    if (radiance)
+        if (int rc = reserve(ctx, ctx->out_rad, npix * sizeof(float) * 4)) return rc;
+    int rc = vrt_cuda_render_device(ctx, frame, image ? (uint32_t *)ctx->out_image.p : nullptr, radiance ? (float *)ctx->out_rad.p : nullptr, stats);
+    if (rc) return rc;
+    const FrameGeom &G = ctx->geom;
+    const size_t row0 = (size_t)G.row_begin, rows = (size_t)(G.row_end - G.row_begin);
+    if (image) CU(cudaMemcpyAsync(image + row0 * G.W, (uint32_t *)ctx->out_image.p + row0 * G.W, rows * G.W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (radiance) CU(cudaMemcpyAsync(radiance + row0 * G.W * 4, (float *)ctx->out_rad.p + row0 * G.W * 4, rows * G.W * sizeof(float) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vrt_cuda_frame_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats)
+{
+    if (int rc = vrt_cuda_tile(ctx, frame)) return rc;
+    return vrt_cuda_render(ctx, frame, image, radiance, stats);
+}
+} // extern "C"

@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libvrt_cuda.so), against the oracle.
+
+Tolerance of BASELINE.json's north_star: max abs per-channel radiance error <= 1e-3 and PSNR >= 60 dB against the
+reference's scalar path with the same erf variant.  Index work (tile membership) is compared exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+from oracle_lib import Oracle, Ref
+from parity_util import channel_diff_lsb, oracle_radiance, pack_image, psnr, reference_lists
+
+pytestmark = pytest.mark.gpu
+
+TOL_ABS = 1e-3
+TOL_PSNR = 60.0
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def check(rad_gpu, rad_ref, what):
+    err = float(np.abs(rad_gpu.astype(np.float64) - rad_ref.astype(np.float64)).max())
+    p = psnr(rad_gpu, rad_ref)
+    print(f"{what}: max abs {err:.3e}, PSNR {p:.1f} dB, peak radiance {float(np.max(rad_ref)):.3e}")
+    assert err <= TOL_ABS, f"{what}: max abs error {err}"
+    assert p >= TOL_PSNR, f"{what}: PSNR {p}"
+    return err
+
+
+def all_pixels(W, H, step=1):
+    return np.arange(0, W * H, step, dtype=np.uint64)
+
+
+def gpu_at(rad, pix, W):
+    return rad.reshape(-1, 4)[np.asarray(pix, np.int64)]
+
+
+# ---------------------------------------------------------------- config 1: -g 4, 256x256, 16 tiles
+@pytest.mark.parametrize("mode,variant", [("MODE8", 1), ("MODE5", 0)])
+def test_config1_tiled(pkg, renderer, mode, variant):
+    V = pkg.vrt
+    scene = pkg.scenes.grid(4)
+    cam, origin = V.camera_t.app(256, 256)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 256, 256, getattr(V, mode), (16, 16))
+    img, rad, st = renderer.frame_render(f, True, True)
+    pix = all_pixels(256, 256)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, variant, tiles=16)
+    check(gpu_at(rad, pix, 256), ref, f"config1 {mode}")
+    # 9 of 16 Gaussians in every tile: 256^2 * 5 * 81 listed terms
+    assert st["terms_listed"] == 256 * 256 * 5 * 81
+    assert 0 < st["terms_executed"] <= st["terms_listed"]
+    # framebuffer: same packing rule applied to the oracle's radiance, within 1 LSB (quantisation amplifies rounding)
+    want = pack_image(ref.reshape(256, 256, 4), mode == "MODE8", mode == "MODE8")
+    assert channel_diff_lsb(img, want) <= 1
+    if mode == "MODE8":
+        assert (img >> 24).max() < 0xFF  # alpha quirk of the tiled SIMD entry (rt.h:373-377)
+    else:
+        assert np.all((img >> 24) == 0xFF)
+
+
+@pytest.mark.parametrize("mode,variant", [("MODE4", 1), ("MODE1", 0)])
+def test_config1_untiled(pkg, renderer, mode, variant):
+    V = pkg.vrt
+    scene = pkg.scenes.grid(4)
+    cam, origin = V.camera_t.app(256, 256)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 256, 256, getattr(V, mode))
+    img, rad, st = renderer.frame_render(f, True, True)
+    pix = all_pixels(256, 256, 3)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, variant)
+    check(gpu_at(rad, pix, 256), ref, f"config1 {mode}")
+    assert st["terms_listed"] == 256 * 256 * 5 * 256
+    assert np.all((img >> 24) == 0xFF)
+
+
+@pytest.mark.skipif(not Ref.available(), reason="compiled reference (oracle/_ref) not present")
+def test_config1_against_compiled_reference(pkg, renderer):
+    """The real reference, run here: mode 8 image (SIMD path) and scalar A&S radiance vs the CUDA path."""
+    V = pkg.vrt
+    scene = pkg.scenes.grid(4)
+    cam, origin = V.camera_t.app(256, 256)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 256, 256, V.MODE8, (16, 16))
+    img, rad, _ = renderer.frame_render(f, True, True)
+    ref_img, _, terms = Ref.render_app(8, scene, 256, 256, tiles=16, threads=4)
+    assert terms == 256 * 256 * 5 * 81
+    assert channel_diff_lsb(img, ref_img) <= 1
+    assert int(img[128, 128]) >> 24 == int(ref_img[128, 128]) >> 24 or abs((int(img[128, 128]) >> 24) - (int(ref_img[128, 128]) >> 24)) <= 1
+    pix = all_pixels(256, 256, 7)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, tiles=16, use_ref=True)
+    check(gpu_at(rad, pix, 256), ref, "config1 vs compiled reference (scalar A&S)")
+
+
+# ---------------------------------------------------------------- tile membership = tile_gaussians
+def _membership_case(pkg, renderer, scene, view, tiles, W=256, H=256):
+    V = pkg.vrt
+    renderer.set_gaussians(scene)
+    f = renderer.frame(view, (0, 0, -4, 0), W, H, V.MODE5, (tiles, tiles))
+    renderer.tile(f)
+    counts, idx = renderer.get_lists()
+    want = reference_lists(scene, view, tiles)
+    assert len(counts) == tiles * tiles
+    offs = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    mism = 0
+    for t in range(tiles * tiles):
+        got = idx[offs[t] : offs[t + 1]]
+        if not np.array_equal(got, want[t]):
+            mism += len(np.setxor1d(got, want[t]))
+    return mism, int(sum(len(w) for w in want))
+
+
+def test_membership_config1(pkg, renderer):
+    cam, _ = pkg.vrt.camera_t.app(256, 256)
+    mism, total = _membership_case(pkg, renderer, pkg.scenes.grid(4), cam.view_matrix, 16)
+    assert mism == 0 and total == 256 * 9
+
+
+def test_membership_img_error_scene(pkg, renderer):
+    # tests/img-error.cpp:27: tile_gaussians(1/8, 1/8, grid16, mat4(1))
+    mism, total = _membership_case(pkg, renderer, pkg.scenes.img_error_grid(), np.eye(4, dtype=np.float32).reshape(16), 16)
+    assert mism == 0 and total > 0
+
+
+def test_membership_grid64_and_rotated(pkg, renderer):
+    scene = pkg.scenes.grid(64)
+    cam, _ = pkg.vrt.camera_t.app(512, 512)
+    mism, total = _membership_case(pkg, renderer, scene, cam.view_matrix, 16, 512, 512)
+    assert mism == 0 and total > 0
+    cam, _ = pkg.vrt.camera_t.app(512, 512, rotation=33.0)
+    mism, total = _membership_case(pkg, renderer, scene, cam.view_matrix, 32, 512, 512)
+    # knife-edge members can flip with the reference's -ffast-math contraction; none expected on this scene
+    assert mism <= total * 1e-4
+
+
+@pytest.mark.parametrize("name", ["sphere", "cube", "monkey", "teapot"])
+def test_membership_objects(pkg, renderer, name):
+    scene = np.load(os.path.join(GOLDEN, f"{name}_gaussians.npy"))
+    cam, _ = pkg.vrt.camera_t.app(256, 256)
+    mism, total = _membership_case(pkg, renderer, scene, cam.view_matrix, 16)
+    assert mism <= max(1, total * 1e-4), (mism, total)
+
+
+# ---------------------------------------------------------------- img-error.cpp procedure on the GPU
+def test_img_error_procedure(pkg, renderer):
+    """tests/img-error.cpp: reference = tiled scalar exact-erf image, test = tiled SIMD A&S image; metric = MSE over RGB of
+    the 8-bit images.  The CUDA path must reproduce both sides: each within 1 LSB of the oracle's packing."""
+    V = pkg.vrt
+    scene = pkg.scenes.img_error_grid()
+    view = np.eye(4, dtype=np.float32).reshape(16)
+    origin = np.zeros(4, np.float32)
+    renderer.set_gaussians(scene)
+    out = {}
+    for mode, variant in (("MODE5", 0), ("MODE8", 1)):
+        f = renderer.frame(view, origin, 256, 256, getattr(V, mode), (16, 16))
+        img, rad, _ = renderer.frame_render(f, True, True)
+        pix = all_pixels(256, 256, 5)
+        ref = oracle_radiance(scene, view, origin, 256, 256, pix, variant, tiles=16)
+        check(gpu_at(rad, pix, 256), ref, f"img-error scene {mode}")
+        out[mode] = img
+    rgb = lambda im: np.stack([(im >> s) & 0xFF for s in (0, 8, 16)], -1).astype(np.float64) / 255.0
+    mse = float(np.mean(np.sum((rgb(out["MODE5"]) - rgb(out["MODE8"])) ** 2, -1)))
+    print(f"img-error MSE (exact vs A&S, GPU): {mse:.3e}")
+    assert mse < 1e-4
+
+
+# ---------------------------------------------------------------- OBJ scenes
+@pytest.mark.parametrize("name,step", [("sphere", 13), ("cube", 61), ("monkey", 97)])
+def test_objects_tiled(pkg, renderer, name, step):
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, f"{name}_gaussians.npy"))
+    cam, origin = V.camera_t.app(256, 256)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 256, 256, V.MODE8, (16, 16))
+    _, rad, st = renderer.frame_render(f, False, True)
+    pix = all_pixels(256, 256, step)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, tiles=16)
+    check(gpu_at(rad, pix, 256), ref, f"{name} MODE8")
+    # the bounded lists give the same picture with far fewer terms
+    fb = renderer.frame(cam.view_matrix, origin, 256, 256, (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (16, 16))
+    _, radb, stb = renderer.frame_render(fb, False, True)
+    d = float(np.abs(radb - rad).max())
+    print(f"{name}: reference lists {st['terms_listed']:.3e} terms -> bounded {stb['terms_listed']:.3e}; max |diff| {d:.2e}")
+    assert d <= 2e-5
+    assert stb["terms_listed"] < st["terms_listed"]
+
+
+def test_teapot_subsample(pkg, renderer):
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, "teapot_gaussians.npy"))
+    cam, origin = V.camera_t.app(256, 256)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 256, 256, (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (16, 16))
+    _, rad, _ = renderer.frame_render(f, False, True)
+    pix = all_pixels(256, 256, 1543)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, tiles=16)
+    check(gpu_at(rad, pix, 256), ref, "teapot REFERENCE_BOUND vs reference lists")
+
+
+# ---------------------------------------------------------------- structural properties
+def test_host_tile_lists_equal_device_lists(pkg, renderer):
+    """vrt_cuda_set_tile_lists (the tiles_t drop-in) and vrt_cuda_tile (K1) must render identical images."""
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, "cube_gaussians.npy"))
+    cam, origin = V.camera_t.app(128, 128)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 128, 128, V.MODE8, (8, 8))
+    img_a, rad_a, _ = renderer.frame_render(f, True, True)
+    lists = reference_lists(scene, cam.view_matrix, 8)
+    renderer.set_tile_lists(f, [scene[l] for l in lists])
+    img_b, rad_b, _ = renderer.render(f, True, True)
+    assert np.array_equal(img_a, img_b)
+    assert np.array_equal(rad_a, rad_b)
+
+
+def test_skip_and_variants_agree(pkg, renderer):
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, "monkey_gaussians.npy"))
+    cam, origin = V.camera_t.app(128, 128)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 128, 128, V.MODE8, (8, 8))
+    _, base, st0 = renderer.frame_render(f, False, True)
+    f2 = renderer.frame(cam.view_matrix, origin, 128, 128, V.MODE8 | V.NO_SKIP, (8, 8))
+    _, noskip, st1 = renderer.frame_render(f2, False, True)
+    assert np.array_equal(base, noskip)  # skipped terms are exactly zero
+    assert st1["terms_executed"] == st1["terms_listed"]
+    assert st0["terms_executed"] <= st1["terms_executed"]
+    try:
+        for q, p in ((2, 0), (2, 1), (4, 0), (6, 1), (8, 1), (8, 0)):
+            renderer.set_tuning(q, p)
+            _, r, _ = renderer.frame_render(f, False, True)
+            assert float(np.abs(r - base).max()) <= 2e-6, (q, p)
+    finally:
+        renderer.set_tuning(4, 1)
+
+
+def test_row_bands_compose(pkg, renderer):
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, "sphere_gaussians.npy"))
+    cam, origin = V.camera_t.app(128, 128)
+    renderer.set_gaussians(scene)
+    flags = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+    f = renderer.frame(cam.view_matrix, origin, 128, 128, flags, (8, 8))
+    img, rad, st = renderer.frame_render(f, True, True)
+    img2 = np.zeros_like(img)
+    rad2 = np.zeros_like(rad)
+    terms = 0.0
+    for rows in ((0, 48), (48, 112), (112, 128)):
+        fb = renderer.frame(cam.view_matrix, origin, 128, 128, flags, (8, 8), rows=rows)
+        renderer.tile(fb)
+        _, _, s = renderer.render(fb, True, True, image=img2, radiance=rad2)
+        terms += s["terms_listed"]
+    assert np.array_equal(img, img2) and np.array_equal(rad, rad2)
+    assert terms == st["terms_listed"]
+
+
+def test_bound_mode_matches_all(pkg, renderer):
+    V = pkg.vrt
+    scene = pkg.scenes.synthetic(3000, 7, -1.9, -1.3)
+    cam, origin = V.camera_t.app(256, 256)
+    renderer.set_gaussians(scene)
+    fa = renderer.frame(cam.view_matrix, origin, 256, 256, V.MODE4)
+    fb = renderer.frame(cam.view_matrix, origin, 256, 256, (V.MODE4 & ~V.LIST_MASK) | V.LIST_BOUND)
+    _, ra, sa = renderer.frame_render(fa, False, True)
+    _, rb, sb = renderer.frame_render(fb, False, True)
+    d = float(np.abs(ra - rb).max())
+    print(f"ALL {sa['terms_listed']:.3e} -> BOUND {sb['terms_listed']:.3e} listed terms, max |diff| {d:.2e}")
+    assert d <= 2e-5
+    pix = all_pixels(256, 256, 499)
+    ref64 = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, f64=True)
+    check(gpu_at(rb, pix, 256), ref64, "synthetic 3000 BOUND vs fp64 oracle")
+
+
+def test_errors_are_reported(pkg, renderer):
+    V = pkg.vrt
+    cam, origin = V.camera_t.app(100, 100)
+    renderer.set_gaussians(pkg.scenes.grid(4))
+    with pytest.raises(V.VrtCudaError):
+        renderer.tile(renderer.frame(cam.view_matrix, origin, 100, 100, V.MODE8, (16, 16)))  # 100 % 16 != 0
+    with pytest.raises(V.VrtCudaError):
+        renderer.tile(renderer.frame(np.zeros(16, np.float32), origin, 64, 64, V.MODE8, (4, 4)))  # singular view
+    f = renderer.frame(cam.view_matrix, origin, 96, 96, V.MODE8, (4, 4))
+    renderer.tile(f)
+    cam2, origin2 = V.camera_t.app(96, 96, rotation=10.0)
+    with pytest.raises(V.VrtCudaError):
+        renderer.render(renderer.frame(cam2.view_matrix, origin2, 96, 96, V.MODE8, (4, 4)))  # camera moved: lists are stale
+
+
+def test_empty_scene_and_ragged_image(pkg, renderer):
+    V = pkg.vrt
+    cam, origin = V.camera_t.app(100, 52)
+    renderer.set_gaussians(np.zeros((0, 10), np.float32))
+    f = renderer.frame(cam.view_matrix, origin, 100, 52, V.MODE4)
+    img, rad, st = renderer.frame_render(f, True, True)
+    assert np.all(rad == 0) and np.all(img == 0xFF000000) and st["terms_listed"] == 0
+    # image not a multiple of the 8x4 cell, tiles of 25x13 pixels
+    scene = pkg.scenes.grid(4)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, 100, 52, V.MODE8, (4, 4))
+    _, rad, _ = renderer.frame_render(f, False, True)
+    pix = all_pixels(100, 52)
+    lists = reference_lists(scene, cam.view_matrix, 4)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, 100, 52, pix, 1, tiles=4, lists=lists)
+    check(gpu_at(rad, pix, 100), ref, "ragged 100x52 image, 25x13 tiles")

@@ -1,0 +1,173 @@
+"""CPU tests: pin the oracle (oracle/vrt_oracle.c) against the reference's outputs.
+
+Two sources of truth: tests/golden/reference_outputs.npz (generated from the unmodified reference by
+tests/golden/make_golden.py) and, when present, the compiled reference itself (oracle/_ref).
+fp32 results of a -ffast-math build are only reproducible to rounding, so float comparisons carry a tolerance
+(stated per test); index work (tile membership, packing) is compared exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+from oracle_lib import Oracle, Ref
+from parity_util import oracle_radiance, pack_image, reference_lists
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "reference_outputs.npz"))
+
+
+def test_as_erf_matches_reference(gold):
+    got = Oracle.as_erf(gold["erf_x"])
+    assert np.abs(got - gold["erf_as"]).max() <= 5e-7  # fast-math (FMA contraction) vs strict IEEE: a few ulp
+    # known property of A&S 7.1.27: |erf_as - erf| <= 5e-4
+    from math import erf
+
+    assert max(abs(float(g) - erf(float(x))) for g, x in zip(got, gold["erf_x"])) <= 6e-4
+
+
+def test_app_camera_matches_reference(gold):
+    for row in gold["app_cameras"]:
+        off, focal, rot = (float(v) for v in row[:3])
+        view, origin = Oracle.app_camera(off, focal, rot)
+        assert np.abs(view - row[3:19]).max() <= 2e-6, (rot, view, row[3:19])
+        assert np.abs(origin - row[19:23]).max() <= 2e-6
+
+
+def test_camera_view_matches_reference(gold):
+    for row in gold["camera_views"]:
+        view = Oracle.view_matrix(row[0:3], float(row[3]), float(row[4]), float(row[5]))
+        assert np.abs(view - row[6:22]).max() <= 2e-6
+
+
+def test_inverse4():
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        m = rng.normal(size=(4, 4)).astype(np.float32) + 3 * np.eye(4, dtype=np.float32)
+        inv = Oracle.inverse4(m.T.reshape(16)).reshape(4, 4).T  # column-major in and out
+        assert np.abs(inv @ m - np.eye(4)).max() <= 1e-4
+
+
+def test_transmittance_sweep_matches_reference(gold, pkg):
+    """tests/transmittance.cpp: 3 Gaussians, origin (0,0,-5), dir +z, s = mu_bar_2 + k sigma_2."""
+    tg = pkg.scenes.transmittance_test()
+    o, d = np.array([0, 0, -5, 0], np.float32), np.array([0, 0, 1, 0], np.float32)
+    for variant, key in ((0, "tr_T_exact"), (1, "tr_T_as")):
+        got = Oracle.transmittance(tg, o, d, gold["tr_s"], variant)
+        assert np.abs(got - gold[key]).max() <= 5e-6, key
+        got64 = Oracle.transmittance(tg, o, d, gold["tr_s"], variant, f64=True)
+        assert np.abs(got64 - gold[key]).max() <= 5e-6, key
+    # T is non-increasing in s and T(0+) <= 1
+    T = Oracle.transmittance(tg, o, d, gold["tr_s"], 0, f64=True)
+    assert np.all(np.diff(T) <= 1e-12)
+
+
+def test_membership_matches_reference(gold, pkg):
+    scene = pkg.scenes.grid(4)
+    view, _ = Oracle.app_camera()
+    tw = np.float32(2.0) / np.float32(16)
+    w, h, counts, idx = Oracle.tile_membership(tw, tw, scene, view)
+    assert (w, h) == (16, 16)
+    assert np.array_equal(counts, gold["c1_counts"]) and np.array_equal(idx, gold["c1_idx"])
+    assert np.all(counts == 9)
+    w, h, counts, idx = Oracle.tile_membership(np.float32(1 / 8), np.float32(1 / 8), pkg.scenes.img_error_grid(), np.eye(4, dtype=np.float32).reshape(16))
+    assert np.array_equal(counts, gold["ie_counts"]) and np.array_equal(idx, gold["ie_idx"])
+    for name in ("teapot", "cube"):
+        g = np.load(os.path.join(GOLDEN, f"{name}_gaussians.npy"))
+        w, h, counts, idx = Oracle.tile_membership(tw, tw, g, view)
+        assert np.array_equal(counts, gold[f"{name}_counts"]), name
+        assert np.array_equal(idx, gold[f"{name}_idx"].astype(np.uint32)), name
+
+
+def test_pixel_dirs_match_reference(gold):
+    view, origin = Oracle.app_camera()
+    dirs = Oracle.pixel_dirs(view, origin, 256, 256, gold["c1_pix"])
+    assert np.abs(dirs - gold["c1_dirs"]).max() <= 3e-7
+    assert np.abs(np.linalg.norm(dirs, axis=1) - 1).max() <= 2e-7
+
+
+def test_radiance_matches_reference_config1(gold, pkg):
+    scene = pkg.scenes.grid(4)
+    view, origin = Oracle.app_camera()
+    pix = gold["c1_pix"]
+    for variant, key in ((0, "c1_rad_exact"), (1, "c1_rad_as")):
+        got = oracle_radiance(scene, view, origin, 256, 256, pix, variant, tiles=16)
+        err = np.abs(got - gold[key]).max()
+        assert err <= 1e-5, (key, err)  # fast-math reference vs IEEE restatement: ~2e-5 relative
+        got64 = oracle_radiance(scene, view, origin, 256, 256, pix, variant, tiles=16, f64=True)
+        assert np.abs(got64 - gold[key]).max() <= 1e-5, key
+    got = oracle_radiance(scene, view, origin, 256, 256, pix, 1)
+    assert np.abs(got - gold["c1_rad_untiled_as"]).max() <= 1e-5
+
+
+def test_radiance_matches_reference_cube(gold):
+    g = np.load(os.path.join(GOLDEN, "cube_gaussians.npy"))
+    view, origin = Oracle.app_camera()
+    lists = reference_lists(g, view, 16)
+    got = oracle_radiance(g, view, origin, 256, 256, gold["cube_pix"], 1, tiles=16, lists=lists)
+    assert np.abs(got - gold["cube_rad_as"]).max() <= 1e-4 * max(1.0, float(gold["cube_rad_as"].max()))  # n~190 terms, fast-math vs IEEE
+
+
+def test_packing_reproduces_reference_images(gold, pkg):
+    """Oracle radiance + orc_pack_pixel rule vs the reference's own u32 images (modes 1/4/5/8), within 1 LSB per channel
+    (the reference's modes differ among themselves by 1 LSB: truncation amplifies fast-math rounding)."""
+    scene = pkg.scenes.grid(4)
+    view, origin = Oracle.app_camera()
+    pix = np.arange(256 * 256, dtype=np.uint64)
+    for mode, variant, tiles, nearest, quirk in ((8, 1, 16, True, True), (5, 0, 16, False, False), (4, 1, None, True, False)):
+        rad = oracle_radiance(scene, view, origin, 256, 256, pix, variant, tiles=tiles).reshape(256, 256, 4)
+        img = pack_image(rad, nearest, quirk)
+        ref = gold[f"c1_image_mode{mode}"]
+        for sh in (0, 8, 16, 24):
+            d = np.abs(((img >> sh) & 0xFF).astype(int) - ((ref >> sh) & 0xFF).astype(int))
+            assert d.max() <= 1, (mode, sh)
+            assert (d > 0).mean() < 0.02, (mode, sh)
+    assert int(gold["c1_image_mode8"][128, 128]) == 0x04020002  # SURVEY.md hard part D
+    assert int(gold["c1_image_mode4"][128, 128]) == 0xFF020002
+    # scalar pack rule == C implementation
+    for rgba in ([0.5, 0.25, 1.5, 0.1], [0.0019, 0.9999, 0.00196, 2.0]):
+        for nearest in (0, 1):
+            for quirk in (0, 1):
+                assert Oracle.pack_pixel(rgba, nearest, quirk) == int(pack_image(np.array(rgba, np.float32).reshape(1, 1, 4), nearest, quirk)[0, 0])
+
+
+def test_terms_of_reference_modes(gold):
+    assert gold["c1_terms_mode8"][0] == 256 * 256 * 5 * 81 == gold["c1_terms_mode5"][0]
+    assert gold["c1_terms_mode4"][0] == 256 * 256 * 5 * 256
+
+
+def test_read_obj_matches_reference(tmp_path):
+    src = np.load(os.path.join(GOLDEN, "sphere_gaussians.npy"))
+    p = tmp_path / "s.obj"
+    with open(p, "w") as f:
+        f.write("# test\no Icosphere\n")
+        for g in src:
+            f.write("v %.6f %.6f %.6f\n" % (g[4], g[5], g[6]))
+        f.write("vn 0 0 1\nf 1 2 3\n")
+    got = Oracle.read_obj(str(p))
+    assert got.shape == src.shape
+    assert np.abs(got - src).max() <= 1e-6
+
+
+@pytest.mark.skipif(not Ref.available(), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_against_compiled_reference_live(pkg):
+    """Live cross-check on inputs that are not in the golden set (rotated camera, monkey.obj Gaussians)."""
+    g = np.load(os.path.join(GOLDEN, "monkey_gaussians.npy"))
+    view_r, origin_r = Ref.app_camera(-4.0, 1.0, 40.0, 64, 64)
+    view_o, origin_o = Oracle.app_camera(-4.0, 1.0, 40.0)
+    assert np.abs(view_r - view_o).max() <= 2e-6
+    tw = np.float32(2.0) / np.float32(8)
+    a = Ref.tile_membership(tw, tw, g, view_r)
+    b = Oracle.tile_membership(tw, tw, g, view_r)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    pix = np.arange(0, 64 * 64, 37, dtype=np.uint64)
+    dirs = Oracle.pixel_dirs(view_r, origin_r, 64, 64, pix)
+    for variant in (0, 1):
+        r = Ref.radiance(g[:120], origin_r, dirs, variant)
+        o = Oracle.radiance(g[:120], origin_r, dirs, variant)
+        o64 = Oracle.radiance(g[:120], origin_r, dirs, variant, f64=True)
+        assert np.abs(r - o).max() <= 5e-5, variant
+        assert np.abs(r - o64).max() <= 5e-5, variant
