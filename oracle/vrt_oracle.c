@@ -84,7 +84,7 @@ ORC_API float orc_transmittance_f32(const float *o, const float *n, float s, con
     return expf(T);
 }
 
-ORC_API double orc_transmittance_f64(const float *o, const float *n, double s, const float *g, uint64_t count, int variant)
+static double transmittance_f64_d(const float *o, const double *n, double s, const float *g, uint64_t count, int variant)
 {
     double T = 0.0;
     for (uint64_t j = 0; j < count; ++j)
@@ -101,6 +101,12 @@ ORC_API double orc_transmittance_f64(const float *o, const float *n, double s, c
         T += sigma * c_bar * (double)INV_SQRT_2_PI_F * (erf1 - erf2);
     }
     return exp(T);
+}
+
+ORC_API double orc_transmittance_f64(const float *o, const float *n, double s, const float *g, uint64_t count, int variant)
+{
+    const double nd[4] = {n[0], n[1], n[2], n[3]};
+    return transmittance_f64_d(o, nd, s, g, count, variant);
 }
 
 /* ---------------------------------------------------------------- radiance ------------------ */
@@ -133,7 +139,7 @@ ORC_API void orc_radiance_f32(const float *o, const float *n, const float *g, ui
     memcpy(out, L, sizeof(L));
 }
 
-ORC_API void orc_radiance_f64(const float *o, const float *n, const float *g, uint64_t count, int variant, double *out)
+static void radiance_f64_d(const float *o, const double *n, const float *g, uint64_t count, int variant, double *out)
 {
     double L[4] = {0, 0, 0, 0};
     for (uint64_t i = 0; i < count; ++i)
@@ -144,13 +150,32 @@ ORC_API void orc_radiance_f64(const float *o, const float *n, const float *g, ui
         for (int k = -4; k <= 0; ++k)
         {
             const double s = ((double)q[G_MX] - o[0]) * n[0] + ((double)q[G_MY] - o[1]) * n[1] + ((double)q[G_MZ] - o[2]) * n[2] + ((double)q[G_MW] - o[3]) * n[3] + k * lambda;
-            const double T = orc_transmittance_f64(o, n, s, g, count, variant);
+            const double T = transmittance_f64_d(o, n, s, g, count, variant);
             const double dx = o[0] + n[0] * s - q[G_MX], dy = o[1] + n[1] * s - q[G_MY], dz = o[2] + n[2] * s - q[G_MZ], dw = o[3] + n[3] * s - q[G_MW];
             inner += (double)q[G_MAG] * exp(-(dx * dx + dy * dy + dz * dz + dw * dw) / (2.0 * lambda * lambda)) * T * lambda;
         }
         for (int c = 0; c < 4; ++c) L[c] += (double)q[G_AR + c] * inner;
     }
     memcpy(out, L, sizeof(L));
+}
+
+/* The formulas in double on the fp32 direction as given (|n| = 1 only to fp32 rounding) ... */
+ORC_API void orc_radiance_f64(const float *o, const float *n, const float *g, uint64_t count, int variant, double *out)
+{
+    const double nd[4] = {n[0], n[1], n[2], n[3]};
+    radiance_f64_d(o, nd, g, count, variant, out);
+}
+
+/* ... and on the direction re-normalised in double: the closed form assumes |n| = 1 exactly (its
+ * oc_sqnorm - mu_bar^2 is the squared ray-centre distance only then), so for small sigma at large depth the
+ * fp32 normalisation error of n alone moves the result by O(|oc|^2 eps / sigma^2).  This entry is the
+ * arbiter for such scenes (DESIGN.md "numerical conditioning"). */
+ORC_API void orc_radiance_f64_unit(const float *o, const float *n, const float *g, uint64_t count, int variant, double *out)
+{
+    double nd[4] = {n[0], n[1], n[2], n[3]};
+    const double len = sqrt(nd[0] * nd[0] + nd[1] * nd[1] + nd[2] * nd[2] + nd[3] * nd[3]);
+    for (int i = 0; i < 4; ++i) nd[i] /= len;
+    radiance_f64_d(o, nd, g, count, variant, out);
 }
 
 /* Batched: rays x one list, spread over host threads (pthreads; no OpenMP runtime in the image).
@@ -171,7 +196,8 @@ static void *ray_worker(void *p)
     const ray_job_t *j = (const ray_job_t *)p;
     for (uint64_t r = (uint64_t)j->tid; r < j->n_rays; r += (uint64_t)j->nthreads)
     {
-        if (j->is64) orc_radiance_f64(j->o, j->dirs + 4 * r, j->g, j->count, j->variant, (double *)j->out + 4 * r);
+        if (j->is64 == 2) orc_radiance_f64_unit(j->o, j->dirs + 4 * r, j->g, j->count, j->variant, (double *)j->out + 4 * r);
+        else if (j->is64) orc_radiance_f64(j->o, j->dirs + 4 * r, j->g, j->count, j->variant, (double *)j->out + 4 * r);
         else orc_radiance_f32(j->o, j->dirs + 4 * r, j->g, j->count, j->variant, (float *)j->out + 4 * r);
     }
     return NULL;
@@ -201,6 +227,11 @@ ORC_API void orc_radiance_rays_f32(const float *o, const float *dirs, uint64_t n
 ORC_API void orc_radiance_rays_f64(const float *o, const float *dirs, uint64_t n_rays, const float *g, uint64_t count, int variant, double *out)
 {
     run_rays(o, dirs, n_rays, g, count, variant, 1, out);
+}
+
+ORC_API void orc_radiance_rays_f64_unit(const float *o, const float *dirs, uint64_t n_rays, const float *g, uint64_t count, int variant, double *out)
+{
+    run_rays(o, dirs, n_rays, g, count, variant, 2, out);
 }
 
 /* ---------------------------------------------------------------- camera -------------------- */

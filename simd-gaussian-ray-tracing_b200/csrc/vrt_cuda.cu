@@ -681,7 +681,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_render(const RenderArgs args
                 alb[e] = r->c;
                 float mu, ee;
                 occluder_setup(a, b, ray, mu, ee);
-                if (e == 0) s0 = __shfl_sync(0xffffffffu, mu, 0); // one depth shift per warp keeps s r - m small
+                if (e == 0)
+                {
+                    // one depth shift per warp keeps s r - m small; a degenerate lane-0 ray must not poison the warp
+                    s0 = __shfl_sync(0xffffffffu, mu, 0);
+                    s0 = (fabsf(s0) <= 3.0e38f) ? s0 : 0.f;
+                }
                 // emission weight sigma c_bar = Kl e / (sqrt(pi/2) log2e)
                 wgt[e] = real ? b.z * ee * (1.f / (SQRT_PI_2 * LOG2E)) : 0.f;
                 any_emit |= real && (ee > args.skip_thresh);

@@ -56,6 +56,7 @@ class Oracle:
             L.orc_transmittance_f64.argtypes = [vp, vp, c_d, vp, c_u64, c_i]
             L.orc_radiance_rays_f32.argtypes = [vp, vp, c_u64, vp, c_u64, c_i, vp]
             L.orc_radiance_rays_f64.argtypes = [vp, vp, c_u64, vp, c_u64, c_i, vp]
+            L.orc_radiance_rays_f64_unit.argtypes = [vp, vp, c_u64, vp, c_u64, c_i, vp]
             L.orc_view_matrix.argtypes = [vp, c_f, c_f, c_f, vp]
             L.orc_app_camera.argtypes = [c_f, c_f, c_f, vp, vp]
             L.orc_inverse4.argtypes = [vp, vp]
@@ -83,10 +84,13 @@ class Oracle:
 
     @classmethod
     def radiance(cls, gaussians, origin, dirs, variant=0, f64=False):
+        """f64=False: fp32 IEEE evaluation; True: double on the fp32 directions as given; "unit": double on the
+        directions re-normalised in double (the arbiter for ill-conditioned scenes)."""
         L = cls.lib()
         g, o, d = _f32(gaussians), _f32(origin), _f32(dirs)
         out = np.zeros((len(d), 4), np.float64 if f64 else np.float32)
-        (L.orc_radiance_rays_f64 if f64 else L.orc_radiance_rays_f32)(_ptr(o), _ptr(d), len(d), _ptr(g), len(g), variant, _ptr(out))
+        fn = L.orc_radiance_rays_f64_unit if f64 == "unit" else (L.orc_radiance_rays_f64 if f64 else L.orc_radiance_rays_f32)
+        fn(_ptr(o), _ptr(d), len(d), _ptr(g), len(g), variant, _ptr(out))
         return out
 
     @classmethod

@@ -17,7 +17,19 @@ def reference_lists(scene, view, tiles):
     return [idx[offs[t] : offs[t + 1]] for t in range(tiles * tiles)]
 
 
-def oracle_radiance(scene, view, origin, W, H, pix, variant, tiles=None, lists=None, f64=False, use_ref=False):
+def near_rays(scene, origin, dirs, k_sigma):
+    """Indices of the Gaussians within k_sigma standard deviations of ANY of the rays `dirs` (n,4) from `origin`.
+    Dropping the rest changes nothing representable: their weight is < exp(-k_sigma^2/2)."""
+    oc = scene[:, 4:7].astype(np.float64) - np.asarray(origin, np.float64)[:3]
+    n = np.asarray(dirs, np.float64)[:, :3]
+    n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    mu = oc @ n.T  # (N, rays)
+    d2 = np.maximum((oc**2).sum(1)[:, None] - mu**2, 0.0)
+    keep = (d2 < (k_sigma * scene[:, 8:9].astype(np.float64)) ** 2).any(1)
+    return np.nonzero(keep)[0]
+
+
+def oracle_radiance(scene, view, origin, W, H, pix, variant, tiles=None, lists=None, f64=False, use_ref=False, near_sigmas=None):
     """Radiance (len(pix), 4) of the reference's scalar path radiance<transmittance<expf, ERF>> at pixel ids `pix`.
     tiles=None: every Gaussian for every pixel (untiled modes); else the pixel's reference-tile list (or `lists`).
     use_ref=True evaluates the compiled reference (oracle/_ref) instead of the restatement."""
@@ -31,7 +43,11 @@ def oracle_radiance(scene, view, origin, W, H, pix, variant, tiles=None, lists=N
         return Oracle.radiance(lst, origin, d, variant, f64)
 
     if tiles is None:
-        out[:] = ev(scene, dirs)
+        if near_sigmas is None:
+            out[:] = ev(scene, dirs)
+        else:  # per-ray prefilter (keeps the O(n^2) oracle affordable on big scenes)
+            for k in range(len(pix)):
+                out[k] = ev(scene[near_rays(scene, origin, dirs[k : k + 1], near_sigmas)], dirs[k : k + 1])[0]
         return out
     if lists is None:
         lists = reference_lists(scene, view, tiles)
@@ -40,10 +56,12 @@ def oracle_radiance(scene, view, origin, W, H, pix, variant, tiles=None, lists=N
     tids = (rows // th_px) * tiles + cols // tw_px
     for t in np.unique(tids):
         sel = np.nonzero(tids == t)[0]
-        lst = scene[lists[t]]
-        if len(lst) == 0:
+        ids = np.asarray(lists[t], np.int64)
+        if near_sigmas is not None and len(ids):
+            ids = ids[np.isin(ids, near_rays(scene, origin, dirs[sel], near_sigmas))]
+        if len(ids) == 0:
             continue
-        out[sel] = ev(lst, dirs[sel])
+        out[sel] = ev(scene[ids], dirs[sel])
     return out
 
 

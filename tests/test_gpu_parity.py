@@ -142,25 +142,50 @@ def test_membership_objects(pkg, renderer, name):
 
 # ---------------------------------------------------------------- img-error.cpp procedure on the GPU
 def test_img_error_procedure(pkg, renderer):
-    """tests/img-error.cpp: reference = tiled scalar exact-erf image, test = tiled SIMD A&S image; metric = MSE over RGB of
-    the 8-bit images.  The CUDA path must reproduce both sides: each within 1 LSB of the oracle's packing."""
+    """tests/img-error.cpp: 16x16 grid (sigma 1/4, magnitude 3), tiles from tile_gaussians(1/8, 1/8, grid, mat4(1)) (:27),
+    camera_create_info_t{} at the origin (:30), reference = tiled scalar exact-erf image (:34), test = tiled SIMD A&S image
+    (:41); metric = MSE over RGB of the 8-bit images (:45-58).  The tiling view differs from the render camera, so the lists
+    go through the tiles_t drop-in (vrt_cuda_set_tile_lists) after K1 built them with the identity view."""
     V = pkg.vrt
     scene = pkg.scenes.img_error_grid()
-    view = np.eye(4, dtype=np.float32).reshape(16)
+    ident = np.eye(4, dtype=np.float32).reshape(16)
     origin = np.zeros(4, np.float32)
+    cam = V.camera_t((0, 0, 0), -90.0, 0.0, 256, 256, 1.0)
     renderer.set_gaussians(scene)
+    renderer.tile(renderer.frame(ident, origin, 256, 256, V.MODE5, (16, 16)))
+    counts, idx = renderer.get_lists()
+    offs = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    lists = [idx[offs[t] : offs[t + 1]] for t in range(256)]
+    want = reference_lists(scene, ident, 16)
+    assert all(np.array_equal(a, b) for a, b in zip(lists, want))
     out = {}
     for mode, variant in (("MODE5", 0), ("MODE8", 1)):
-        f = renderer.frame(view, origin, 256, 256, getattr(V, mode), (16, 16))
-        img, rad, _ = renderer.frame_render(f, True, True)
+        f = renderer.frame(cam.view_matrix, origin, 256, 256, getattr(V, mode), (16, 16))
+        renderer.set_tile_lists(f, [scene[l] for l in lists])
+        img, rad, _ = renderer.render(f, True, True)
         pix = all_pixels(256, 256, 5)
-        ref = oracle_radiance(scene, view, origin, 256, 256, pix, variant, tiles=16)
+        ref = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, variant, tiles=16, lists=lists)
         check(gpu_at(rad, pix, 256), ref, f"img-error scene {mode}")
         out[mode] = img
     rgb = lambda im: np.stack([(im >> s) & 0xFF for s in (0, 8, 16)], -1).astype(np.float64) / 255.0
     mse = float(np.mean(np.sum((rgb(out["MODE5"]) - rgb(out["MODE8"])) ** 2, -1)))
     print(f"img-error MSE (exact vs A&S, GPU): {mse:.3e}")
     assert mse < 1e-4
+
+
+def test_degenerate_ray_does_not_poison_its_cell(pkg, renderer):
+    """Identity view + origin 0 makes the centre pixel's ray 0/0 (NaN in the reference too); only that pixel may be NaN."""
+    V = pkg.vrt
+    scene = pkg.scenes.img_error_grid()
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    origin = np.zeros(4, np.float32)
+    renderer.set_gaussians(scene)
+    for mode, variant in (("MODE5", 0), ("MODE8", 1)):
+        f = renderer.frame(ident, origin, 256, 256, getattr(V, mode), (16, 16))
+        _, rad, _ = renderer.frame_render(f, False, True)
+        pix = np.array([r * 256 + c for r in range(126, 134) for c in range(124, 140) if (r, c) != (128, 128)], np.uint64)
+        ref = oracle_radiance(scene, ident, origin, 256, 256, pix, variant, tiles=16)
+        check(gpu_at(rad, pix, 256), ref, f"cell of the degenerate ray, {mode}")
 
 
 # ---------------------------------------------------------------- OBJ scenes
@@ -254,6 +279,13 @@ def test_row_bands_compose(pkg, renderer):
 
 
 def test_bound_mode_matches_all(pkg, renderer):
+    """Small-sigma scene.  (1) the bounded lists change nothing visible; (2) parity against the arbiter.
+
+    On such scenes the reference's own fp32 scalar path is NOT reproducible to 1e-3: its d^2 = |oc|^2 - mu_bar^2 cancels
+    ~|oc|^2/sigma^2 ~ 4e5 and assumes |n| = 1 exactly, so the fp32 normalisation error of the ray alone moves the result
+    by > 1e-3 (measured below; DESIGN.md "numerical conditioning").  The CUDA path computes the ray-centre distance from
+    the perpendicular component instead and is checked against the closed form evaluated in double on exactly-unit rays;
+    the reference-side restatements are required to be FARTHER from that arbiter than the CUDA path is."""
     V = pkg.vrt
     scene = pkg.scenes.synthetic(3000, 7, -1.9, -1.3)
     cam, origin = V.camera_t.app(256, 256)
@@ -265,9 +297,15 @@ def test_bound_mode_matches_all(pkg, renderer):
     d = float(np.abs(ra - rb).max())
     print(f"ALL {sa['terms_listed']:.3e} -> BOUND {sb['terms_listed']:.3e} listed terms, max |diff| {d:.2e}")
     assert d <= 2e-5
+    assert sb["terms_listed"] < 0.01 * sa["terms_listed"]
     pix = all_pixels(256, 256, 499)
-    ref64 = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, f64=True)
-    check(gpu_at(rb, pix, 256), ref64, "synthetic 3000 BOUND vs fp64 oracle")
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, f64="unit", near_sigmas=12)
+    err_gpu = check(gpu_at(rb, pix, 256), ideal, "synthetic 3000 BOUND vs arbiter (fp64, unit rays)")
+    assert err_gpu <= 5e-5
+    ref32 = oracle_radiance(scene, cam.view_matrix, origin, 256, 256, pix, 1, near_sigmas=12)
+    err_ref = float(np.abs(ref32 - ideal).max())
+    print(f"reference formula in fp32 vs arbiter: {err_ref:.3e}  (CUDA path: {err_gpu:.3e})")
+    assert err_ref > err_gpu
 
 
 def test_errors_are_reported(pkg, renderer):
