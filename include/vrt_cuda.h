@@ -162,6 +162,10 @@ int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, u
  * Q in {2,4,6,8} and packed f32x2 arithmetic on (1) / off (0).  Defaults are the tuned values. */
 int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
 
+/* Roofline probe: FP32 FMA throughput of the context's GPU in TFLOP/s (FMA = 2 flops), measured with
+ * independent FFMA chains (packed_f32x2 = 0) or FFMA2 chains (1).  bench.py reports it beside the nominal peak. */
+int vrt_cuda_fp32_peak(vrt_cuda_ctx *ctx, int packed_f32x2, double *tflops_out);
+
 int vrt_cuda_sync(vrt_cuda_ctx *ctx);
 /* The context's cudaStream_t as an integer (for ordering NCCL / torch work after a render_device). */
 uint64_t vrt_cuda_stream(vrt_cuda_ctx *ctx);

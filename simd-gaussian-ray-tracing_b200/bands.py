@@ -1,0 +1,59 @@
+"""Multi-GPU row bands: the image shards into contiguous row bands, one per rank.
+
+Pixels are independent and the only shared input is the (read-only) Gaussian array, so the data path needs exactly
+two exchanges per scene / frame and no halo:
+    * one broadcast of the scene (n x 40 B) from rank 0 when it changes          -- torch.distributed.broadcast
+    * one gather of the finished u32 bands to rank 0 per frame                   -- grouped send/recv (bands differ in size)
+One process per GPU; NCCL over NVLink on the GPU box, gloo in the CPU tests.  Band boundaries come from the per-row
+cost K1 reports (sum of pixels * 5 * n^2 per cell row), split by vrt_host_row_bands so the slowest rank's share is minimal.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+
+
+def split_rows(row_cost, row_px, n_parts, height, align):
+    """Work-balanced band boundaries in PIXEL rows.
+
+    row_cost[i] is the cost of pixel rows [i*row_px, (i+1)*row_px); boundaries are multiples of `align` pixels (a
+    multiple of row_px: tile rows keep every cell inside one band).  Returns n_parts+1 ascending pixel rows."""
+    row_cost = np.asarray(row_cost, np.float64)
+    if align % row_px:
+        raise ValueError("align must be a multiple of the cost row height")
+    group = align // row_px
+    n_groups = (len(row_cost) + group - 1) // group
+    cost = np.zeros(n_groups, np.float64)
+    for g in range(n_groups):
+        cost[g] = row_cost[g * group : (g + 1) * group].sum()
+    # a small per-row constant keeps empty regions from collapsing into zero-height bands
+    cost = cost + max(cost.sum(), 1.0) * 1e-6
+    out = np.zeros(n_parts + 1, np.uint32)
+    rc = _ffi.host_lib().vrt_host_row_bands(cost.ctypes.data_as(ctypes.c_void_p), n_groups, n_parts, out.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise ValueError("vrt_host_row_bands failed")
+    bounds = [min(int(b) * align, height) for b in out]
+    bounds[-1] = height
+    return bounds
+
+
+def balanced_bands(renderer, n_parts, height, align):
+    """Bands from the row costs of the renderer's last full-frame vrt_cuda_tile()."""
+    rows, row_px = renderer.row_costs()
+    return split_rows(rows, row_px, n_parts, height, align)
+
+
+def gather_bands(image, bounds, rank, world, dist):
+    """Rank r owns rows [bounds[r], bounds[r+1]) of `image` (a [H, W] tensor on every rank); after the call rank 0
+    holds every band.  One grouped batch of point-to-point transfers (ncclSend/ncclRecv under NCCL)."""
+    ops = []
+    if rank == 0:
+        for src in range(1, world):
+            if bounds[src + 1] > bounds[src]:
+                ops.append(dist.P2POp(dist.irecv, image[bounds[src] : bounds[src + 1]], src))
+    elif bounds[rank + 1] > bounds[rank]:
+        ops.append(dist.P2POp(dist.isend, image[bounds[rank] : bounds[rank + 1]], 0))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()

@@ -802,6 +802,35 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_render(const RenderArgs args
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP32 roofline probe: dependent-free FFMA (or FFMA2) chains, the denominator of roofline.frac measured live
+// ------------------------------------------------------------------------------------------------
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b)
+{
+    float2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = make_float2(threadIdx.x * 1e-3f + i, blockIdx.x * 1e-4f - i);
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            if (PACK) v[i] = __ffma2_rn(v[i], aa, bb);
+            else
+            {
+                v[i].x = fmaf(v[i].x, a, b);
+                v[i].y = fmaf(v[i].y, a, b);
+            }
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += v[i].x + v[i].y;
+    if (acc == 12345.678f) out[0] = acc; // never true; keeps the chains alive
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct DevBuf
@@ -1137,6 +1166,29 @@ int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int q, int pack)
     if (q != 2 && q != 4 && q != 6 && q != 8) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 2, 4, 6 or 8");
     ctx->tune_q = q;
     ctx->tune_pack = pack ? 1 : 0;
+    return 0;
+}
+
+// Measures the FP32 FMA throughput of the device (TFLOP/s, FMA = 2 flops) with scalar FFMA (packed = 0) or FFMA2.
+int vrt_cuda_fp32_peak(vrt_cuda_ctx *ctx, int packed, double *tflops_out)
+{
+    if (!ctx || !tflops_out) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep)
+    {
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        if (packed) k_fp32_peak<true><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 0.999f, 0.001f);
+        else k_fp32_peak<false><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 0.999f, 0.001f);
+        CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *tflops_out = (double)blocks * threads * 16.0 * iters * 2.0 / (best * 1e-3) / 1e12;
     return 0;
 }
 

@@ -194,6 +194,11 @@ class Renderer:
         self.tile(frame)
         return self.render(frame, want_image, want_radiance)
 
+    def fp32_peak(self, packed=False):
+        out = ctypes.c_double()
+        self._check(self._lib.vrt_cuda_fp32_peak(self._h, int(packed), ctypes.byref(out)), "vrt_cuda_fp32_peak")
+        return float(out.value)
+
     def sync(self):
         self._check(self._lib.vrt_cuda_sync(self._h), "vrt_cuda_sync")
 

@@ -1,0 +1,82 @@
+"""CPU tests of the multi-GPU host logic: band splitting and the gather of bands to rank 0 (gloo, world_size 2 and 3)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, H, W, result_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    ge.load_package()
+    from vrt_b200 import bands as B
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank derives the same bands from the same (synthetic) cost profile: cost grows quadratically down the image
+    row_px = 4
+    cost = (np.arange(H // row_px, dtype=np.float64) + 1) ** 2
+    bounds = B.split_rows(cost, row_px, world, H, align=16)
+    assert bounds[0] == 0 and bounds[-1] == H and all(b % 16 == 0 for b in bounds[:-1])
+    # "scene broadcast": rank 0 owns the data, everyone receives it
+    scene = torch.arange(50, dtype=torch.float32).reshape(5, 10) if rank == 0 else torch.zeros(5, 10)
+    dist.broadcast(scene, 0)
+    assert float(scene[4, 9]) == 49.0
+    # "render": each rank fills ONLY its band with a function of (row, col, scene)
+    image = torch.full((H, W), -1, dtype=torch.int32)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    rows = torch.arange(r0, r1, dtype=torch.int32)[:, None]
+    cols = torch.arange(W, dtype=torch.int32)[None, :]
+    image[r0:r1] = rows * 1000 + cols + int(scene[0, 1].item())
+    B.gather_bands(image, bounds, rank, world, dist)
+    if rank == 0:
+        want = torch.arange(H, dtype=torch.int32)[:, None] * 1000 + cols + 1
+        ok = bool(torch.equal(image, want))
+        band_cost = [float(cost[bounds[i] // row_px : bounds[i + 1] // row_px].sum()) for i in range(world)]
+        with open(result_path, "w") as f:
+            f.write(f"{int(ok)} {max(band_cost) / (cost.sum() / world):.4f} {' '.join(map(str, bounds))}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_bands_gather_gloo(world, tmp_path):
+    import torch.multiprocessing as mp
+
+    H, W = 256, 64
+    result = str(tmp_path / "res.txt")
+    mp.spawn(_worker, args=(world, _free_port(), H, W, result), nprocs=world, join=True)
+    ok, imbalance, *bounds = open(result).read().split()
+    assert ok == "1"
+    assert float(imbalance) < 1.25, f"bands {bounds} are unbalanced: {imbalance}"
+
+
+def test_split_rows_properties(pkg):
+    from vrt_b200 import bands as B
+
+    # uniform cost -> equal bands; alignment respected; empty tail rows still assigned
+    b = B.split_rows(np.ones(64), 4, 4, 256, 16)
+    assert b == [0, 64, 128, 192, 256]
+    b = B.split_rows(np.r_[np.zeros(32), np.ones(32)], 4, 2, 256, 32)
+    assert b[0] == 0 and b[-1] == 256 and b[1] % 32 == 0 and 128 < b[1] < 256
+    with pytest.raises(ValueError):
+        B.split_rows(np.ones(64), 4, 2, 256, 6)
+    # more ranks than aligned rows: bands may be empty but stay ordered and cover the image
+    b = B.split_rows(np.ones(8), 4, 4, 32, 16)
+    assert b[0] == 0 and b[-1] == 32 and all(x <= y for x, y in zip(b, b[1:]))
