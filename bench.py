@@ -260,9 +260,24 @@ def run_cuda(args, pkg, cfg, rank, world):
     k2 = torch.tensor([k2_ms, k1_ms, stats[0]["terms_executed"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(k2, op=dist.ReduceOp.MAX)
-    if rank != 0:
+    def cleanup():
+        # ordered teardown: tensors that live on the context's stream must be released before the stream is destroyed
+        # (the pinned-host allocator records an event on every stream a block was used on when the block is freed)
+        nonlocal dev_scene, image, host_image, host_scene, k2
+        import gc
+
+        r.sync()
+        torch.cuda.synchronize()
+        dev_scene = image = host_image = host_scene = k2 = None
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
         if world > 1:
             dist.destroy_process_group()
+        r.close()
+
+    if rank != 0:
+        cleanup()
         return
 
     value = terms_exec / (ms * 1e-3)
@@ -305,8 +320,7 @@ def run_cuda(args, pkg, cfg, rank, world):
         line["cpu_baseline"] = {"value": cb["terms"] / best, "unit": "evals/s", "cores": threads, "kind": cb["kind"],
                                 "sample": f"{cb['n_tiles']} reference tiles of {cb['tile_px']}x{cb['tile_px']} px (mean list {cb['mean_list']:.0f}), {cb['terms']:.3e} evaluations, best of 2; {cb['what']}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    cleanup()
 
 
 def main():
