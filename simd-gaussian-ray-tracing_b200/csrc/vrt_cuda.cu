@@ -597,8 +597,8 @@ __device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, c
     e = ex2_approx(-d2 * b.y);
 }
 
-template <int ERF, int Q, bool PACK>
-__global__ void __launch_bounds__(K2_WARPS * 32) k2_render(const RenderArgs args)
+template <int ERF, int Q, bool PACK, int MINB>
+__global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
 {
     __shared__ WarpStage s_stage[K2_WARPS];
     const FrameGeom &G = c_geom;
@@ -872,7 +872,7 @@ struct vrt_cuda_ctx
     uint32_t launches = 0;
     float ms_tile = 0.f;
     // tuning
-    int tune_q = 4;
+    int tune_q = 0; // 0 = automatic: 8 emitters per register block, 4 when the lists are short
     int tune_pack = 1;
 };
 
@@ -1052,28 +1052,40 @@ int build_queue(vrt_cuda_ctx *ctx)
     return 0;
 }
 
-template <int ERF, int Q, bool PACK>
+template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1)>
 void launch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK>, K2_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB>, K2_WARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-    k2_render<ERF, Q, PACK><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+    k2_render<ERF, Q, PACK, MINB><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
 }
 
 template <int ERF>
 int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
-    const int q = ctx->tune_q;
+    // Q = 8 (236 registers, 8 warps/SM) measured fastest on B200: instruction-level parallelism across 40 independent
+    // sample chains per thread beats occupancy (tools/tune_k2.py); short lists waste less padding with Q = 4
+    const int q = ctx->tune_q ? ctx->tune_q : ((ctx->n_lists && ctx->n_entries / ctx->n_lists >= 24) ? 8 : 4);
     const bool p = ctx->tune_pack != 0;
+    // experimental occupancy variants: pack = 2 / 3 -> packed math with >= 3 / 4 CTAs per SM (register cap 80 / 64)
+    if (ctx->tune_pack >= 2)
+    {
+        const int q = ctx->tune_q;
+        if (q == 4 && ctx->tune_pack == 2) { launch_k2<ERF, 4, true, 3>(ctx, a); return 0; }
+        if (q == 2 && ctx->tune_pack == 2) { launch_k2<ERF, 2, true, 3>(ctx, a); return 0; }
+        if (q == 2 && ctx->tune_pack == 3) { launch_k2<ERF, 2, true, 4>(ctx, a); return 0; }
+        return fail(ctx, VRT_CUDA_E_INVALID, "no occupancy variant for Q=%d pack=%d", q, ctx->tune_pack);
+    }
     switch (q)
     {
     case 2: p ? launch_k2<ERF, 2, true>(ctx, a) : launch_k2<ERF, 2, false>(ctx, a); break;
     case 4: p ? launch_k2<ERF, 4, true>(ctx, a) : launch_k2<ERF, 4, false>(ctx, a); break;
     case 6: p ? launch_k2<ERF, 6, true>(ctx, a) : launch_k2<ERF, 6, false>(ctx, a); break;
     case 8: p ? launch_k2<ERF, 8, true>(ctx, a) : launch_k2<ERF, 8, false>(ctx, a); break;
+    case 10: launch_k2<ERF, 10, true>(ctx, a); break;
     default: return fail(ctx, VRT_CUDA_E_INVALID, "unsupported emitter block %d", q);
     }
     return 0;
@@ -1163,9 +1175,9 @@ int vrt_cuda_set_gaussians_device(vrt_cuda_ctx *ctx, const float *aos_dev, uint6
 int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int q, int pack)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
-    if (q != 2 && q != 4 && q != 6 && q != 8) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 2, 4, 6 or 8");
+    if (q != 0 && q != 2 && q != 4 && q != 6 && q != 8 && q != 10) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 0 (auto), 2, 4, 6, 8 or 10");
     ctx->tune_q = q;
-    ctx->tune_pack = pack ? 1 : 0;
+    ctx->tune_pack = pack;
     return 0;
 }
 

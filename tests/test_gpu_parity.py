@@ -255,7 +255,7 @@ def test_skip_and_variants_agree(pkg, renderer):
             _, r, _ = renderer.frame_render(f, False, True)
             assert float(np.abs(r - base).max()) <= 2e-6, (q, p)
     finally:
-        renderer.set_tuning(4, 1)
+        renderer.set_tuning(0, 1)  # back to the automatic choice
 
 
 def test_row_bands_compose(pkg, renderer):
