@@ -1,0 +1,98 @@
+"""GPU tests of the callers either side of the hot path: the headless `volumetric-ray-tracer` and the C++ drop-in header."""
+import os
+import re
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+from oracle_lib import Ref
+from parity_util import channel_diff_lsb
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "simd-gaussian-ray-tracing_b200", "csrc", "volumetric-ray-tracer")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def read_png(path):
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, size = 8, b"", None
+    while pos < len(data):
+        ln, typ = struct.unpack(">I4s", data[pos : pos + 8])
+        body = data[pos + 8 : pos + 8 + ln]
+        if typ == b"IHDR":
+            size = struct.unpack(">II", body[:8])
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + ln
+    w, h = size
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 4 * w)
+    return rows[:, 1:].copy().view(np.uint32).reshape(h, w)  # bytes are the little-endian 0xAARRGGBB words (main.cpp:306)
+
+
+def run_app(args, cwd):
+    r = subprocess.run([APP] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    return r.stdout
+
+
+def test_app_config1_matches_reference_image(tmp_path):
+    """BASELINE config 1: `-g 4 -q -o out.png` at 256x256 -- mode 8 against the reference's own mode-8 image (golden)."""
+    gold = np.load(os.path.join(GOLDEN, "reference_outputs.npz"))
+    out = run_app(["-q", "-g", "4", "-m", "8", "-o", "out.png"], str(tmp_path))
+    assert re.search(r"^TIME: [0-9.e+-]+ ms$", out, re.M), out
+    img = read_png(str(tmp_path / "out.png"))
+    assert img.shape == (256, 256)
+    assert channel_diff_lsb(img, gold["c1_image_mode8"]) <= 1
+    # default mode (10: reference lists AND 6-sigma bound) renders the same picture
+    run_app(["-q", "-g", "4", "-o", "b.png"], str(tmp_path))
+    assert channel_diff_lsb(read_png(str(tmp_path / "b.png")), gold["c1_image_mode8"]) <= 1
+    # scalar modes: truncating quantisation, opaque alpha
+    run_app(["-q", "-g", "4", "-m", "5", "-o", "m5.png"], str(tmp_path))
+    m5 = read_png(str(tmp_path / "m5.png"))
+    assert channel_diff_lsb(m5, gold["c1_image_mode5"]) <= 1 and np.all((m5 >> 24) == 0xFF)
+    run_app(["-q", "-g", "4", "-m", "4", "-o", "m4.png"], str(tmp_path))
+    assert channel_diff_lsb(read_png(str(tmp_path / "m4.png")), gold["c1_image_mode4"]) <= 1
+
+
+def test_app_frames_orbit_and_flags(tmp_path, pkg, renderer):
+    out = run_app(["-q", "-g", "6", "-w", "128", "--frames", "3", "-r", "90", "-i", "15", "--tiles", "8", "-c", "-5", "--focal-length", "1.2", "-m", "8", "-o", "turn.png"], str(tmp_path))
+    assert re.search(r"^AVG\. TIME: [0-9.e+-]+ ms \(3 frames\)$", out, re.M), out
+    V = pkg.vrt
+    scene = pkg.scenes.grid(6)
+    renderer.set_gaussians(scene)
+    for k in range(3):
+        img = read_png(str(tmp_path / f"turn_{k + 1}.png"))  # name_<frame>.ext (main.cpp:302)
+        cam, origin = V.camera_t.app(128, 128, -5.0, 1.2, 15.0 + k * 30.0)
+        f = renderer.frame(cam.view_matrix, origin, 128, 128, V.MODE8, (8, 8))
+        want, _, _ = renderer.frame_render(f, True, False)
+        assert channel_diff_lsb(img, want) <= 1, k
+
+
+def test_app_obj_and_synthetic(tmp_path, pkg):
+    src = np.load(os.path.join(GOLDEN, "sphere_gaussians.npy"))
+    with open(tmp_path / "s.obj", "w") as f:
+        for g in src:
+            f.write("v %.6f %.6f %.6f\n" % (g[4], g[5], g[6]))
+    out = run_app(["-q", "-f", "s.obj", "-w", "64", "-o", "s.png", "--tiles", "4"], str(tmp_path))
+    assert "42 Gaussians" in out
+    assert read_png(str(tmp_path / "s.png")).shape == (64, 64)
+    out = run_app(["-q", "--synthetic", "20000", "--seed", "5", "--sigma-range", "-2.0,-1.5", "-w", "512", "--tiles", "32", "-o", "r.png"], str(tmp_path))
+    assert "20000 Gaussians" in out
+    img = read_png(str(tmp_path / "r.png"))
+    assert ((img >> 16) & 0xFF).max() > 50  # something was drawn
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_check")), reason="oracle/_ref/dropin_check not built")
+def test_dropin_with_reference_types():
+    """oracle/dropin_check.cpp: the reference's own camera_t / gaussians_t / tiles_t objects passed to vrt::cuda_* entries,
+    CPU image vs CUDA image for modes 8, 5, 4 and device-side tiling."""
+    if Ref.path() is None:
+        pytest.skip("host CPU cannot run the compiled reference")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "dropin_check"), "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0 and "dropin_check: PASSED" in r.stdout, r.stdout
