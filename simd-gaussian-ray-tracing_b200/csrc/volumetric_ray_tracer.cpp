@@ -71,7 +71,7 @@ struct cmd_args_t
         int lidx;
         for (;;)
         {
-            const int c = getopt_long(argc, argv, "r:m:qw:o:f:g::h:t:c:i:", opts, &lidx);
+            const int c = getopt_long(argc, argv, "r:m:qw:o:f:g:h:t:c:i:", opts, &lidx);
             if (c == -1) break;
             switch (c)
             {
