@@ -166,6 +166,13 @@ int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
  * independent FFMA chains (packed_f32x2 = 0) or FFMA2 chains (1).  bench.py reports it beside the nominal peak. */
 int vrt_cuda_fp32_peak(vrt_cuda_ctx *ctx, int packed_f32x2, double *tflops_out);
 
+/* Roofline probe: ceiling of K2's inner-term instruction mix (terms/s) with `pairs` (5, 10, 20) independent packed
+ * pairs per thread and `ctas_per_sm` resident 256-thread CTAs -- no loads, setup or control flow. */
+int vrt_cuda_term_peak(vrt_cuda_ctx *ctx, int pairs, int ctas_per_sm, double *terms_per_s_out);
+
+/* Pipe-mix probe: chain steps/s where one step = nf FFMA2 + nm MUFU.RCP + nl LOP3 (a few fixed combinations). */
+int vrt_cuda_mix_peak(vrt_cuda_ctx *ctx, int nf, int nm, int nl, double *steps_per_s_out);
+
 int vrt_cuda_sync(vrt_cuda_ctx *ctx);
 /* The context's cudaStream_t as an integer (for ordering NCCL / torch work after a render_device). */
 uint64_t vrt_cuda_stream(vrt_cuda_ctx *ctx);

@@ -17,6 +17,10 @@
 
 #include <cuda_runtime.h>
 
+#ifndef VRT_SIGN_EARLY
+#define VRT_SIGN_EARLY 0
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -155,8 +159,15 @@ __device__ __forceinline__ float2 erf_variant2(float2 t)
         d = __fmul2_rn(d, d);
         d = __fmul2_rn(d, d);
         const float2 rc = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+#if VRT_SIGN_EARLY
+        // sign(t) as +-1 taken before the reciprocal, so the ALU op does not sit behind the MUFU scoreboard:
+        // erf = sg - sg * rc
+        const float2 sg = make_float2(copysign_bits(1.f, t.x), copysign_bits(1.f, t.y));
+        return __ffma2_rn(rc, make_float2(-sg.x, -sg.y), sg);
+#else
         const float2 v = __ffma2_rn(rc, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
         return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
+#endif
     }
     else
     {
@@ -597,7 +608,7 @@ __device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, c
     e = ex2_approx(-d2 * b.y);
 }
 
-template <int ERF, int Q, bool PACK, int MINB>
+template <int ERF, int Q, bool PACK, int MINB, int JU>
 __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
 {
     __shared__ WarpStage s_stage[K2_WARPS];
@@ -715,6 +726,55 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                     }
                     __syncwarp();
                 }
+                if (JU == 2)
+                {
+                    // two occluders per step: 2 x 5Q independent term chains in flight with only 5Q accumulators, i.e. the
+                    // instruction-level parallelism of a 2Q block at the register cost of Q (keeps 16 warps/SM at Q = 4)
+                    for (uint32_t j = 0; j < cnt; j += 2)
+                    {
+                        const uint32_t j1 = min(j + 1, cnt - 1);
+                        const float4 a0 = st.a[j], b0 = st.b[j], a1 = st.a[j1], b1 = st.b[j1];
+                        float mu0, e0, mu1, e1;
+                        occluder_setup(a0, b0, ray, mu0, e0);
+                        occluder_setup(a1, b1, ray, mu1, e1);
+                        const bool two = j + 1 < cnt;
+                        const bool go0 = __any_sync(0xffffffffu, e0 > args.skip_thresh);
+                        const bool go1 = two && __any_sync(0xffffffffu, e1 > args.skip_thresh);
+                        if (!(go0 || go1)) continue; // warp-uniform skip
+                        exec += n_real * ((go0 ? 1u : 0u) + (go1 ? 1u : 0u));
+                        // an occluder skipped for the warp but riding along with an active partner must add exactly what the
+                        // skip adds: nothing
+                        const float A0 = go0 ? b0.z * e0 : 0.f, A1 = go1 ? b1.z * e1 : 0.f;
+                        const float r0 = b0.x, r1 = b1.x;
+                        const float nm0 = -(mu0 - s0) * r0, nm1 = -(mu1 - s0) * r1;
+                        if (PACK)
+                        {
+                            const float2 rr0 = make_float2(r0, r0), mm0 = make_float2(nm0, nm0), AA0 = make_float2(A0, A0);
+                            const float2 rr1 = make_float2(r1, r1), mm1 = make_float2(nm1, nm1), AA1 = make_float2(A1, A1);
+#pragma unroll
+                            for (int e2 = 0; e2 < Q / 2; ++e2)
+#pragma unroll
+                                for (int k = 0; k < 5; ++k)
+                                {
+                                    const float2 sv = make_float2(s[2 * e2][k], s[2 * e2 + 1][k]);
+                                    const float2 ev0 = erf_variant2<ERF>(__ffma2_rn(sv, rr0, mm0));
+                                    const float2 ev1 = erf_variant2<ERF>(__ffma2_rn(sv, rr1, mm1));
+                                    const float2 ac = __ffma2_rn(AA1, ev1, __ffma2_rn(AA0, ev0, make_float2(acc[2 * e2][k], acc[2 * e2 + 1][k])));
+                                    acc[2 * e2][k] = ac.x;
+                                    acc[2 * e2 + 1][k] = ac.y;
+                                }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int e = 0; e < Q; ++e)
+#pragma unroll
+                                for (int k = 0; k < 5; ++k)
+                                    acc[e][k] = fmaf(A1, erf_variant<ERF>(fmaf(s[e][k], r1, nm1)), fmaf(A0, erf_variant<ERF>(fmaf(s[e][k], r0, nm0)), acc[e][k]));
+                        }
+                    }
+                    continue;
+                }
                 for (uint32_t j = 0; j < cnt; ++j)
                 {
                     const float4 a = st.a[j], b = st.b[j];
@@ -828,6 +888,59 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float 
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc += v[i].x + v[i].y;
     if (acc == 12345.678f) out[0] = acc; // never true; keeps the chains alive
+}
+
+// Inner-term ceiling probe: the exact instruction mix of K2's body (per pair of terms 7 FFMA2 + 2 FMUL2 + 2 MUFU.RCP +
+// 2 LOP3) with NP independent pairs per thread and no loads, setup or control flow around it.
+template <int NP>
+__global__ void __launch_bounds__(256) k_term_peak(float *out, int iters, float r0, float nm0, float a0)
+{
+    float2 s[NP], acc[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+    {
+        s[i] = make_float2(threadIdx.x * 1e-3f + i * 0.37f, blockIdx.x * 1e-4f - i * 0.21f);
+        acc[i] = make_float2(0.f, 0.f);
+    }
+    float r = r0, nm = nm0, A = a0;
+    for (int it = 0; it < iters; ++it)
+    {
+        const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(A, A);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc[i] = __ffma2_rn(AA, erf_variant2<0>(__ffma2_rn(s[i], rr, mm)), acc[i]);
+        r += 1e-4f; nm -= 1e-4f; A += 1e-6f;
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) t += acc[i].x + acc[i].y;
+    if (t == 12345.678f) out[0] = t;
+}
+
+// Pipe-mix probe: NF packed FMAs + NM MUFU.RCP + NL LOP3 per step on 16 independent float2 chains per thread.
+template <int NF, int NM, int NL>
+__global__ void __launch_bounds__(256) k_mix_peak(float *out, int iters, float a, float b)
+{
+    float2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = make_float2(1.f + threadIdx.x * 1e-3f + i, 2.f + blockIdx.x * 1e-4f + i);
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) v[i] = __ffma2_rn(v[i], aa, bb);
+            if (NM >= 1) v[i].x = rcp_approx(v[i].x);
+            if (NM >= 2) v[i].y = rcp_approx(v[i].y);
+            if (NL >= 1) v[i].x = copysign_bits(v[i].x, v[i].y);
+            if (NL >= 2) v[i].y = copysign_bits(v[i].y, aa.x);
+        }
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += v[i].x + v[i].y;
+    if (t == 12345.678f) out[0] = t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1052,15 +1165,15 @@ int build_queue(vrt_cuda_ctx *ctx)
     return 0;
 }
 
-template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1)>
+template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1), int JU = 1>
 void launch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB>, K2_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, JU>, K2_WARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-    k2_render<ERF, Q, PACK, MINB><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+    k2_render<ERF, Q, PACK, MINB, JU><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
 }
 
 template <int ERF>
@@ -1075,6 +1188,9 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     {
         const int q = ctx->tune_q;
         if (q == 4 && ctx->tune_pack == 2) { launch_k2<ERF, 4, true, 3>(ctx, a); return 0; }
+        if (q == 4 && ctx->tune_pack == 4) { launch_k2<ERF, 4, true, 2, 2>(ctx, a); return 0; }
+        if (q == 2 && ctx->tune_pack == 4) { launch_k2<ERF, 2, true, 3, 2>(ctx, a); return 0; }
+        if (q == 6 && ctx->tune_pack == 4) { launch_k2<ERF, 6, true, 1, 2>(ctx, a); return 0; }
         if (q == 2 && ctx->tune_pack == 2) { launch_k2<ERF, 2, true, 3>(ctx, a); return 0; }
         if (q == 2 && ctx->tune_pack == 3) { launch_k2<ERF, 2, true, 4>(ctx, a); return 0; }
         return fail(ctx, VRT_CUDA_E_INVALID, "no occupancy variant for Q=%d pack=%d", q, ctx->tune_pack);
@@ -1201,6 +1317,70 @@ int vrt_cuda_fp32_peak(vrt_cuda_ctx *ctx, int packed, double *tflops_out)
         if (rep > 0 && ms < best) best = ms;
     }
     *tflops_out = (double)blocks * threads * 16.0 * iters * 2.0 / (best * 1e-3) / 1e12;
+    return 0;
+}
+
+// Measures the ceiling of K2's inner-term instruction mix (terms/s) with `pairs` independent FFMA2 pairs per thread.
+int vrt_cuda_term_peak(vrt_cuda_ctx *ctx, int pairs, int ctas_per_sm, double *terms_per_s_out)
+{
+    if (!ctx || !terms_per_s_out) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
+    const int iters = 2048, blocks = ctx->sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1), threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep)
+    {
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        switch (pairs)
+        {
+        case 5: k_term_peak<5><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        case 10: k_term_peak<10><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        case 20: k_term_peak<20><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        default: return fail(ctx, VRT_CUDA_E_INVALID, "pairs must be 5, 10 or 20");
+        }
+        CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *terms_per_s_out = (double)blocks * threads * 2.0 * pairs * iters / (best * 1e-3);
+    return 0;
+}
+
+// Pipe-mix probe: steps/s of (nf packed FMAs, nm MUFU.RCP, nl LOP3) per float2 chain step; see tools/probe_peaks.py.
+int vrt_cuda_mix_peak(vrt_cuda_ctx *ctx, int nf, int nm, int nl, double *steps_per_s_out)
+{
+    if (!ctx || !steps_per_s_out) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
+    const int iters = 1024, blocks = ctx->sm_count * 4, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep)
+    {
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        float *o = (float *)ctx->counter.p;
+        const int key = nf * 100 + nm * 10 + nl;
+        switch (key)
+        {
+        case 900: k_mix_peak<9, 0, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 902: k_mix_peak<9, 0, 2><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 910: k_mix_peak<9, 1, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 920: k_mix_peak<9, 2, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 922: k_mix_peak<9, 2, 2><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 20: k_mix_peak<0, 2, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 120: k_mix_peak<1, 2, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 420: k_mix_peak<4, 2, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        case 1820: k_mix_peak<18, 2, 0><<<blocks, threads, 0, ctx->stream>>>(o, iters, 0.999f, 0.001f); break;
+        default: return fail(ctx, VRT_CUDA_E_INVALID, "unsupported mix %d", key);
+        }
+        CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *steps_per_s_out = (double)blocks * threads * 16.0 * iters / (best * 1e-3);
     return 0;
 }
 

@@ -199,6 +199,16 @@ class Renderer:
         self._check(self._lib.vrt_cuda_fp32_peak(self._h, int(packed), ctypes.byref(out)), "vrt_cuda_fp32_peak")
         return float(out.value)
 
+    def term_peak(self, pairs=20, ctas_per_sm=1):
+        out = ctypes.c_double()
+        self._check(self._lib.vrt_cuda_term_peak(self._h, int(pairs), int(ctas_per_sm), ctypes.byref(out)), "vrt_cuda_term_peak")
+        return float(out.value)
+
+    def mix_peak(self, nf, nm, nl):
+        out = ctypes.c_double()
+        self._check(self._lib.vrt_cuda_mix_peak(self._h, int(nf), int(nm), int(nl), ctypes.byref(out)), "vrt_cuda_mix_peak")
+        return float(out.value)
+
     def sync(self):
         self._check(self._lib.vrt_cuda_sync(self._h), "vrt_cuda_sync")
 

@@ -26,7 +26,7 @@ def main():
     ]
     variants = [(4, 1), (4, 2), (2, 1), (2, 2), (2, 3), (6, 1), (8, 1), (4, 0)]
     if quick:
-        variants = [(8, 1), (10, 1)]
+        variants = [(8, 1), (4, 1), (4, 4), (2, 4), (6, 4)]
     for name, scene_fn, W, flags, tiles, rows in work:
         if only and name != only:
             continue
