@@ -339,3 +339,72 @@ def test_empty_scene_and_ragged_image(pkg, renderer):
     lists = reference_lists(scene, cam.view_matrix, 4)
     ref = oracle_radiance(scene, cam.view_matrix, origin, 100, 52, pix, 1, tiles=4, lists=lists)
     check(gpu_at(rad, pix, 100), ref, "ragged 100x52 image, 25x13 tiles")
+
+
+# ---------------------------------------------------------------- BASELINE configs at full size
+def _full_size_case(pkg, renderer, scene, W, tiles, n_pix, seed):
+    """Renders the full frame with the production lists and checks a pixel subsample against the fp64 unit-ray arbiter fed
+    with {reference tile list of the pixel's tile} intersected with {Gaussians within 12 sigma of the ray}."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import cpu_lists
+
+    V = pkg.vrt
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    flags = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+    f = renderer.frame(cam.view_matrix, origin, W, W, flags, (tiles, tiles), 6.0)
+    img, rad, st = renderer.frame_render(f, True, True)
+    rng = np.random.default_rng(seed)
+    pix = np.unique(rng.integers(0, W * W, n_pix).astype(np.uint64))
+    dirs = Oracle.pixel_dirs(cam.view_matrix, origin, W, W, pix)
+    mx, my, sg, valid = cpu_lists.projected(scene, cam.view_matrix)
+    cxs, tw = cpu_lists.tile_centres(tiles)
+    tile_px = W // tiles
+    ideal = np.zeros((len(pix), 4))
+    ref32 = np.zeros((len(pix), 4), np.float32)
+    for k, p in enumerate(pix):
+        row, col = int(p) // W, int(p) % W
+        near = np.nonzero(cpu_lists.ray_distance_sigmas(scene, origin, dirs[k : k + 1])[:, 0] < 12.0)[0]
+        member = cpu_lists.reference_member(mx[near], my[near], sg[near], valid[near], cxs[col // tile_px], cxs[row // tile_px], tw, tw)
+        lst = scene[near[member]]
+        if len(lst):
+            ideal[k] = Oracle.radiance(lst, origin, dirs[k : k + 1], 1, "unit")[0]
+            ref32[k] = Oracle.radiance(lst, origin, dirs[k : k + 1], 1)[0]
+    got = gpu_at(rad, pix, W)
+    err = check(got, ideal, f"{len(scene)} Gaussians @{W}^2 vs arbiter")
+    err_ref = float(np.abs(ref32 - ideal).max())
+    print(f"reference formula in fp32 vs arbiter: {err_ref:.3e}; frame: {st['terms_listed']:.3e} listed, {st['terms_executed']:.3e} executed terms, "
+          f"tile {st['ms_tile']:.2f} ms, render {st['ms_render']:.2f} ms, max list {st['max_list']}")
+    # framebuffer: the packed pixel equals the mode-8 packing of the radiance the kernel produced (K3 is exact integer work)
+    assert np.array_equal(img, pack_image(rad, True, True))
+    return err, err_ref, st
+
+
+def test_config4_full_size(pkg, renderer):
+    err, err_ref, st = _full_size_case(pkg, renderer, pkg.scenes.config4(), 4096, 256, 160, 4)
+    assert err <= 1e-4
+    assert st["terms_executed"] <= st["terms_listed"]
+
+
+def test_config5_full_size(pkg, renderer):
+    err, err_ref, st = _full_size_case(pkg, renderer, pkg.scenes.config5(), 4096, 256, 160, 5)
+    assert err <= 1e-4
+    assert err_ref > err  # the reference's own fp32 evaluation is farther from the arbiter (DESIGN.md section 5)
+
+
+def test_config3_grid64_subsample(pkg, renderer):
+    """BASELINE config 3 (64x64 grid, 2048^2, 16 tiles): bounded lists on the GPU vs the reference's scalar path on the pixel's
+    literal reference-tile list (n ~ 1600) for a handful of pixels inside the grid's footprint."""
+    V = pkg.vrt
+    scene = pkg.scenes.grid(64)
+    W = 2048
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, W, W, (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (16, 16), 6.0)
+    _, rad, st = renderer.frame_render(f, False, True)
+    pix = np.array([r * W + c for r in (900, 1023, 1100) for c in (850, 1024, 1187)], np.uint64)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1, tiles=16)
+    check(gpu_at(rad, pix, W), ref, "config3 bounded lists vs reference-tile lists (scalar A&S)")
+    assert st["terms_listed"] < 5.5e13 / 100  # SURVEY.md: 5.5e13 with the reference's lists
