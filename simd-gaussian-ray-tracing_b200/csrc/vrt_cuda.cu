@@ -304,12 +304,23 @@ __device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, co
     return true;
 }
 
-// level 0: children = coarse bins, parent = root segments (identity lists); one warp per (bin, segment)
-// level 1: children = cells, parent = the bin's list; one warp per cell
-// WRITE = false: counts[child * n_seg + seg] ; WRITE = true: indices at offsets[child * n_seg + seg]
-template <bool WRITE, int LEVEL>
-__global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root,
-                                               int n_seg, const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ parent_idx,
+// One culling level.  The cell grid is grouped into gx x gy-cell groups (ngx x ngy of them); every group scans the list of
+// the coarser group that contains it (pgx x pgy cells, pngx per row) and keeps what passes its own test.  The root level
+// has no parent: it scans the scene itself in n_seg segments of ROOT_SEG Gaussians, one warp per (group, segment), and the
+// per-segment pieces concatenate in index order.  The finest level has gx = gy = 1 (one 8x4-pixel cell per warp).
+struct CullLevel
+{
+    int gx, gy, ngx, ngy;
+    int pgx, pgy, pngx;
+    int is_root, n_seg;
+};
+
+// WRITE = false: counts[group * n_seg + seg] ; WRITE = true: indices at offsets[group * n_seg + seg].
+// 32 candidates per step, one per lane: predicate -> ballot -> popc of the lower lanes = ordered slot (lists keep
+// ascending Gaussian index, so K2's sums are reproducible).
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root, const CullLevel L,
+                                               const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ parent_idx,
                                                uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, uint32_t *__restrict__ out_idx,
                                                uint32_t n_work)
 {
@@ -317,42 +328,35 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
     const int lane = threadIdx.x & 31;
     if (wid >= n_work) return;
     const FrameGeom &G = c_geom;
-    const uint32_t child = wid / n_seg, seg = wid % n_seg;
-    int x0, x1, y0, y1;
+    const uint32_t group = wid / L.n_seg, seg = wid % L.n_seg;
+    const int gxi = group % L.ngx, gyi = group / L.ngx;
+    // pixel rect of the group = union of its cells' rects
+    const int cx0 = gxi * L.gx, cx1 = min(G.ncx, cx0 + L.gx) - 1;
+    const int cy0 = gyi * L.gy, cy1 = min(G.ncy, cy0 + L.gy) - 1;
+    const int x0 = (cx0 / G.cptx) * G.tile_w + (cx0 % G.cptx) * CELL_W;
+    const int y0 = (cy0 / G.cpty) * G.tile_h + (cy0 % G.cpty) * CELL_H;
+    const int x1 = min((cx1 / G.cptx) * G.tile_w + min(G.tile_w, (cx1 % G.cptx + 1) * CELL_W), G.W);
+    const int y1 = min((cy1 / G.cpty) * G.tile_h + min(G.tile_h, (cy1 % G.cpty + 1) * CELL_H), G.H);
     uint32_t begin, end;
-    if (LEVEL == 0)
+    if (L.is_root)
     {
-        const int bx = child % G.nbx, by = child / G.nbx;
-        // pixel rect of the bin = union of its cells' rects
-        const int cx0 = bx * BIN_CX, cx1 = min(G.ncx, cx0 + BIN_CX) - 1;
-        const int cy0 = by * BIN_CY, cy1 = min(G.ncy, cy0 + BIN_CY) - 1;
-        x0 = (cx0 / G.cptx) * G.tile_w + (cx0 % G.cptx) * CELL_W;
-        y0 = (cy0 / G.cpty) * G.tile_h + (cy0 % G.cpty) * CELL_H;
-        x1 = min((cx1 / G.cptx) * G.tile_w + min(G.tile_w, (cx1 % G.cptx + 1) * CELL_W), G.W);
-        y1 = min((cy1 / G.cpty) * G.tile_h + min(G.tile_h, (cy1 % G.cpty + 1) * CELL_H), G.H);
         begin = seg * ROOT_SEG;
         end = min(n_root, begin + ROOT_SEG);
     }
     else
     {
-        const int cx = child % G.ncx, cy = child / G.ncx;
-        x0 = (cx / G.cptx) * G.tile_w + (cx % G.cptx) * CELL_W;
-        y0 = (cy / G.cpty) * G.tile_h + (cy % G.cpty) * CELL_H;
-        x1 = min((cx / G.cptx) * G.tile_w + min(G.tile_w, (cx % G.cptx + 1) * CELL_W), G.W);
-        y1 = min((cy / G.cpty) * G.tile_h + min(G.tile_h, (cy % G.cpty + 1) * CELL_H), G.H);
-        const uint32_t bin = (cy / BIN_CY) * G.nbx + (cx / BIN_CX);
-        begin = parent_off[bin];
-        end = parent_off[bin + 1];
+        const uint32_t parent = (uint32_t)((cy0 / L.pgy) * L.pngx + (cx0 / L.pgx));
+        begin = parent_off[parent];
+        end = parent_off[parent + 1];
     }
-    CullRect rc;
-    make_rect(x0, x1, y0, y1, rc);
-    // cells outside the rendered row band get empty lists
-    const bool in_band = (LEVEL == 0) || (y1 > G.row_begin && y0 < G.row_end);
-
+    // groups outside the rendered row band get empty lists
+    const bool in_band = y1 > G.row_begin && y0 < G.row_end;
     uint32_t base = WRITE ? offsets[wid] : 0u;
     uint32_t count = 0;
-    if (in_band)
+    if (in_band && end > begin)
     {
+        CullRect rc;
+        make_rect(x0, x1, y0, y1, rc);
         for (uint32_t k = begin; k < end; k += 32)
         {
             const uint32_t e = k + lane;
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
             uint32_t gi = 0;
             if (e < end)
             {
-                gi = (LEVEL == 0) ? e : parent_idx[e];
+                gi = L.is_root ? e : parent_idx[e];
                 const float4 a = rec[gi].a;
                 const float sigma = rec[gi].b.w;
                 const float4 cr = G.use_ref ? cullrec[gi] : make_float4(0.f, 0.f, 0.f, 1.f);
@@ -376,6 +380,13 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
         }
     }
     if (!WRITE && lane == 0) counts[wid] = count;
+}
+
+// offsets of a segmented root level -> one offset per group (+ the total)
+__global__ void k1_group_offsets(const uint32_t *__restrict__ seg_offsets, uint32_t *__restrict__ group_offsets, uint32_t n_groups, int n_seg)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_groups) group_offsets[i] = seg_offsets[(size_t)i * n_seg];
 }
 
 // pure REFERENCE lists (one list per reference tile), level 1 with children = tiles
@@ -967,7 +978,7 @@ struct vrt_cuda_ctx
     DevBuf aos;        // scene, n x 10 floats
     DevBuf rec;        // frame records
     DevBuf cullrec;    // reference tiling projection
-    DevBuf counts, offsets, idx;          // level 0 (bins)
+    DevBuf lvl_counts[4], lvl_offsets[4], lvl_idx[4], lvl_group_off; // coarse culling levels
     DevBuf ccounts, coffsets, cidx;       // level 1 (cells / tiles)
     DevBuf hist, queue, stats, counter, rowcost;
     DevBuf out_image, out_rad;
@@ -1249,10 +1260,14 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->counts, &ctx->offsets, &ctx->idx, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
+    DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
                       &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 4; ++i)
+        for (DevBuf *b : {&ctx->lvl_counts[i], &ctx->lvl_offsets[i], &ctx->lvl_idx[i]})
+            if (b->p) cudaFree(b->p);
+    if (ctx->lvl_group_off.p) cudaFree(ctx->lvl_group_off.p);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1435,46 +1450,66 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     }
     else
     {
-        // level 0: bins x root segments
-        const uint32_t nbins = (uint32_t)(G.nbx * G.nby);
-        const int nseg = (int)std::max<uint64_t>(1, (N + ROOT_SEG - 1) / ROOT_SEG);
-        const uint64_t work0 = (uint64_t)nbins * nseg;
-        if (work0 > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "scene x image too large for the binning level");
-        if (int rc = reserve(ctx, ctx->counts, sizeof(uint32_t) * work0)) return rc;
-        if (int rc = reserve(ctx, ctx->offsets, sizeof(uint32_t) * (work0 + 1))) return rc;
-        const unsigned g0 = (unsigned)((work0 * 32 + 255) / 256);
-        k1_cull<false, 0><<<g0, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nseg, nullptr, nullptr,
-                                                      (uint32_t *)ctx->counts.p, nullptr, nullptr, (uint32_t)work0);
-        k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->counts.p, (uint32_t *)ctx->offsets.p, (uint32_t)work0);
-        uint32_t total0 = 0;
-        CU(cudaMemcpyAsync(&total0, (const uint32_t *)ctx->offsets.p + work0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (int rc = reserve(ctx, ctx->idx, sizeof(uint32_t) * std::max<uint32_t>(total0, 1))) return rc;
-        k1_cull<true, 0><<<g0, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nseg, nullptr, nullptr, nullptr,
-                                                     (const uint32_t *)ctx->offsets.p, (uint32_t *)ctx->idx.p, (uint32_t)work0);
-        // bin b owns [offsets[b*nseg], offsets[(b+1)*nseg]) : compact the per-bin offsets into counts (reuse as parent_off)
-        // level 1 reads parent_off[bin] = offsets[bin*nseg]; build that strided view with a tiny gather on the host side of the
-        // stream: a 1-thread-per-bin copy kernel is overkill, cudaMemcpy2DAsync does it.
-        if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * ((size_t)G.ncx * G.ncy + nbins + 2))) return rc;
-        uint32_t *bin_off = (uint32_t *)ctx->ccounts.p + (size_t)G.ncx * G.ncy; // nbins + 1 entries after the cell counts
-        CU(cudaMemcpy2DAsync(bin_off, sizeof(uint32_t), ctx->offsets.p, sizeof(uint32_t) * nseg, sizeof(uint32_t), nbins, cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(bin_off + nbins, (const uint32_t *)ctx->offsets.p + work0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-        // level 1: cells
-        const uint32_t ncells = (uint32_t)(G.ncx * G.ncy);
-        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * ((size_t)ncells + 1))) return rc;
-        const unsigned g1 = (unsigned)(((uint64_t)ncells * 32 + 255) / 256);
-        k1_cull<false, 1><<<g1, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, 1, bin_off, (const uint32_t *)ctx->idx.p,
-                                                      (uint32_t *)ctx->ccounts.p, nullptr, nullptr, ncells);
-        k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, ncells);
-        uint32_t total1 = 0;
-        CU(cudaMemcpyAsync(&total1, (const uint32_t *)ctx->coffsets.p + ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(total1, 1))) return rc;
-        k1_cull<true, 1><<<g1, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, 1, bin_off, (const uint32_t *)ctx->idx.p, nullptr,
-                                                     (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ncells);
-        ctx->launches += 6;
-        ctx->n_lists = ncells;
-        ctx->n_entries = total1;
+        // levels from coarse to fine: groups of 64x128, 16x32, 4x8 and 1x1 cells (512, 128, 32 pixels square, then the
+        // 8x4-pixel cell); a level is dropped when it would not be coarser than the whole grid
+        std::vector<CullLevel> levels;
+        const int gxs[4] = {64, 16, 4, 1}, gys[4] = {128, 32, 8, 1};
+        for (int i = 0; i < 4; ++i)
+        {
+            if (i < 3 && gxs[i] >= G.ncx && gys[i] >= G.ncy && !levels.empty()) continue;
+            if (i < 3 && gxs[i + 1] >= G.ncx && gys[i + 1] >= G.ncy) continue; // the next finer level is still one group
+            CullLevel L{};
+            L.gx = gxs[i]; L.gy = gys[i];
+            L.ngx = (G.ncx + L.gx - 1) / L.gx; L.ngy = (G.ncy + L.gy - 1) / L.gy;
+            L.is_root = levels.empty() ? 1 : 0;
+            L.n_seg = L.is_root ? (int)std::max<uint64_t>(1, (N + ROOT_SEG - 1) / ROOT_SEG) : 1;
+            if (!levels.empty()) { L.pgx = levels.back().gx; L.pgy = levels.back().gy; L.pngx = levels.back().ngx; }
+            levels.push_back(L);
+        }
+        const uint32_t *parent_off = nullptr, *parent_idx = nullptr;
+        for (size_t li = 0; li < levels.size(); ++li)
+        {
+            const CullLevel &L = levels[li];
+            const bool last = li + 1 == levels.size();
+            const uint64_t groups = (uint64_t)L.ngx * L.ngy, work = groups * L.n_seg;
+            if (work > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "scene x image too large for culling level %zu", li);
+            DevBuf &cnt = last ? ctx->ccounts : ctx->lvl_counts[li];
+            DevBuf &off = last ? ctx->coffsets : ctx->lvl_offsets[li];
+            DevBuf &idx = last ? ctx->cidx : ctx->lvl_idx[li];
+            if (int rc = reserve(ctx, cnt, sizeof(uint32_t) * work)) return rc;
+            if (int rc = reserve(ctx, off, sizeof(uint32_t) * (work + 1))) return rc;
+            const unsigned grid = (unsigned)((work * 32 + 255) / 256);
+            k1_cull<false><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx,
+                                                         (uint32_t *)cnt.p, nullptr, nullptr, (uint32_t)work);
+            k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)cnt.p, (uint32_t *)off.p, (uint32_t)work);
+            uint32_t total = 0;
+            CU(cudaMemcpyAsync(&total, (const uint32_t *)off.p + work, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (int rc = reserve(ctx, idx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
+            k1_cull<true><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx, nullptr,
+                                                        (const uint32_t *)off.p, (uint32_t *)idx.p, (uint32_t)work);
+            ctx->launches += 3;
+            parent_idx = (const uint32_t *)idx.p;
+            if (L.n_seg > 1)
+            {
+                // per-(group, segment) offsets -> per-group offsets for the next level
+                if (int rc = reserve(ctx, ctx->lvl_group_off, sizeof(uint32_t) * (groups + 1))) return rc;
+                k1_group_offsets<<<(unsigned)((groups + 256) / 256), 256, 0, ctx->stream>>>((const uint32_t *)off.p, (uint32_t *)ctx->lvl_group_off.p, (uint32_t)groups, L.n_seg);
+                ctx->launches++;
+                parent_off = (const uint32_t *)ctx->lvl_group_off.p;
+                if (last)
+                {
+                    // a single-level hierarchy with a segmented root: the cell offsets are the group offsets
+                    CU(cudaMemcpyAsync(ctx->coffsets.p, ctx->lvl_group_off.p, sizeof(uint32_t) * (groups + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+            }
+            else parent_off = (const uint32_t *)off.p;
+            if (last)
+            {
+                ctx->n_lists = (uint32_t)groups;
+                ctx->n_entries = total;
+            }
+        }
     }
     CU(cudaGetLastError());
     if (int rc = build_queue(ctx)) return rc;
