@@ -596,13 +596,45 @@ struct RenderArgs
     uint32_t quant_nearest, alpha_from_w;
 };
 
-// per-warp staging buffer: STAGE records, occluder part (a, b) and emitter part (c)
-struct WarpStage
+// ---- per-warp record staging -------------------------------------------------------------------------------------------
+// Each warp owns two STAGE-record buffers and two mbarriers.  When a list is a contiguous range of `rec` (ALL lists,
+// caller-supplied tiles_t lists) a chunk is one TMA bulk copy (cp.async.bulk global -> shared, completion on the mbarrier)
+// issued by lane 0 one chunk ahead of the compute; index lists are gathered by the lanes (one record per lane).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    float4 a[STAGE];
-    float4 b[STAGE];
-    float4 c[STAGE];
-};
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    // try_wait suspends the thread for a hardware time slice per probe; the probe count is bounded so that a protocol
+    // error traps instead of hanging the GPU
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+    {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    // generic-proxy reads of the buffer (previous chunk) are ordered before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 struct PixelRay
 {
@@ -619,15 +651,24 @@ __device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, c
     e = ex2_approx(-d2 * b.y);
 }
 
-template <int ERF, int Q, bool PACK, int MINB, int JU>
+template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG>
 __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
 {
-    __shared__ WarpStage s_stage[K2_WARPS];
+    __shared__ __align__(128) Rec s_rec[K2_WARPS][2][STAGE];
+    __shared__ __align__(8) unsigned long long s_bar[K2_WARPS][2];
     const FrameGeom &G = c_geom;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpStage &st = s_stage[warp];
     const int lx = lane & (CELL_W - 1), ly = lane >> 3;
     unsigned long long exec = 0;
+    uint32_t par = 0u; // phase parity of this warp's two mbarriers (bit b = buffer b)
+    if (CONTIG && lane == 0)
+    {
+        mbar_init(smem_u32(&s_bar[warp][0]), 1);
+        mbar_init(smem_u32(&s_bar[warp][1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    constexpr bool contiguous = CONTIG; // lists are contiguous ranges of rec (TMA) or index lists (gathered by the lanes)
 
     for (;;)
     {
@@ -664,25 +705,57 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
         };
 
         // ---- pass A: C = sum_j A_j erf(-m_j)   (the sample-independent half of every term) ----
-        float C = 0.f;
-        for (uint32_t j0 = 0; j0 < n; j0 += STAGE)
-        {
-            const uint32_t cnt = min((uint32_t)STAGE, n - j0);
-            __syncwarp();
-            if ((uint32_t)lane < cnt)
+        const uint32_t n_chunks = (n + STAGE - 1) / STAGE;
+        const bool resident = n <= STAGE; // a single chunk stays staged for the whole cell
+        auto chunk_count = [&](uint32_t c) { return min((uint32_t)STAGE, n - c * STAGE); };
+        // TMA: one bulk copy of the chunk's contiguous records into buffer c & 1, completion on that buffer's mbarrier
+        auto issue = [&](uint32_t c) {
+            if (lane == 0)
+                tma_bulk_load(smem_u32(&s_rec[warp][c & 1][0]), args.rec + off + c * STAGE, chunk_count(c) * (uint32_t)sizeof(Rec), smem_u32(&s_bar[warp][c & 1]));
+        };
+        // chunk c ready in its buffer; the next chunk is put in flight first
+        auto acquire = [&](uint32_t c) -> const Rec * {
+            const uint32_t b = c & 1u;
+            if (c + 1 < n_chunks) issue(c + 1);
+            mbar_wait(smem_u32(&s_bar[warp][b]), (par >> b) & 1u);
+            par ^= 1u << b;
+            return &s_rec[warp][b][0];
+        };
+        // index lists: the lanes gather one record each (occluder part only) into buffer 0
+        auto gather = [&](uint32_t c) -> const Rec * {
+            __syncwarp(); // every lane is done with the previous chunk
+            if ((uint32_t)lane < chunk_count(c))
             {
-                const Rec *r = load_rec(j0 + lane);
-                st.a[lane] = r->a;
-                st.b[lane] = r->b;
+                const Rec *r = args.rec + args.list_idx[off + c * STAGE + lane];
+                s_rec[warp][0][lane].a = r->a;
+                s_rec[warp][0][lane].b = r->b;
             }
             __syncwarp();
+            return &s_rec[warp][0][0];
+        };
+        auto begin_pass = [&]() {
+            if (contiguous && n) issue(0);
+        };
+        auto chunk_begin = [&](uint32_t c) -> const Rec * { return contiguous ? acquire(c) : gather(c); };
+        auto chunk_end = [&](uint32_t c) {
+            (void)c;
+            if (contiguous) __syncwarp(); // every lane is done with the buffer before TMA refills it
+        };
+        float C = 0.f;
+        const Rec *sr = &s_rec[warp][0][0];
+        begin_pass();
+        for (uint32_t c = 0; c < n_chunks; ++c)
+        {
+            sr = chunk_begin(c);
+            const uint32_t cnt = chunk_count(c);
             for (uint32_t j = 0; j < cnt; ++j)
             {
-                const float4 a = st.a[j], b = st.b[j];
+                const float4 a = sr[j].a, b = sr[j].b;
                 float mu, e;
                 occluder_setup(a, b, ray, mu, e);
                 C = fmaf(b.z * e, erf_variant<ERF>(-mu * b.x), C);
             }
+            if (!resident) chunk_end(c);
         }
 
         // ---- pass B: emitters in blocks of Q, all occluders per block ----
@@ -722,21 +795,11 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
             if (!__any_sync(0xffffffffu, any_emit)) continue; // no lane sees any of these emitters
             const uint32_t n_real = min((uint32_t)Q, n - q0);
 
-            for (uint32_t j0 = 0; j0 < n; j0 += STAGE)
+            if (!resident) begin_pass();
+            for (uint32_t c = 0; c < n_chunks; ++c)
             {
-                const uint32_t cnt = min((uint32_t)STAGE, n - j0);
-                if (n > STAGE || q0 == 0)
-                {
-                    // (re)stage; lists that fit one stage stay resident from pass A
-                    __syncwarp();
-                    if ((uint32_t)lane < cnt)
-                    {
-                        const Rec *r = load_rec(j0 + lane);
-                        st.a[lane] = r->a;
-                        st.b[lane] = r->b;
-                    }
-                    __syncwarp();
-                }
+                const uint32_t cnt = chunk_count(c);
+                if (!resident) sr = chunk_begin(c); // lists that fit one chunk stay resident from pass A
                 if (JU == 2)
                 {
                     // two occluders per step: 2 x 5Q independent term chains in flight with only 5Q accumulators, i.e. the
@@ -744,7 +807,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                     for (uint32_t j = 0; j < cnt; j += 2)
                     {
                         const uint32_t j1 = min(j + 1, cnt - 1);
-                        const float4 a0 = st.a[j], b0 = st.b[j], a1 = st.a[j1], b1 = st.b[j1];
+                        const float4 a0 = sr[j].a, b0 = sr[j].b, a1 = sr[j1].a, b1 = sr[j1].b;
                         float mu0, e0, mu1, e1;
                         occluder_setup(a0, b0, ray, mu0, e0);
                         occluder_setup(a1, b1, ray, mu1, e1);
@@ -784,11 +847,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                                     acc[e][k] = fmaf(A1, erf_variant<ERF>(fmaf(s[e][k], r1, nm1)), fmaf(A0, erf_variant<ERF>(fmaf(s[e][k], r0, nm0)), acc[e][k]));
                         }
                     }
+                    if (!resident) chunk_end(c);
                     continue;
                 }
                 for (uint32_t j = 0; j < cnt; ++j)
                 {
-                    const float4 a = st.a[j], b = st.b[j];
+                    const float4 a = sr[j].a, b = sr[j].b;
                     float mu, e;
                     occluder_setup(a, b, ray, mu, e);
                     if (!__any_sync(0xffffffffu, e > args.skip_thresh)) continue; // warp-uniform skip
@@ -824,6 +888,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                             for (int k = 0; k < 5; ++k) acc[e][k] = fmaf(A, erf_variant<ERF>(fmaf(s[e][k], r, nm)), acc[e][k]);
                     }
                 }
+                if (!resident) chunk_end(c);
             }
             // T(s) = 2^(C - acc); pdf at the samples = c_bar e^{-k^2/2}, k = -4..0 (src/vrt/rt.h:153-161)
 #pragma unroll
@@ -1176,15 +1241,22 @@ int build_queue(vrt_cuda_ctx *ctx)
     return 0;
 }
 
-template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1), int JU = 1>
-void launch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
+template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG>
+void launch_k2c(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, JU>, K2_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, JU, CONTIG>, K2_WARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-    k2_render<ERF, Q, PACK, MINB, JU><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+    k2_render<ERF, Q, PACK, MINB, JU, CONTIG><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+}
+
+template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1), int JU = 1>
+void launch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
+{
+    if (a.list_idx == nullptr) launch_k2c<ERF, Q, PACK, MINB, JU, true>(ctx, a);
+    else launch_k2c<ERF, Q, PACK, MINB, JU, false>(ctx, a);
 }
 
 template <int ERF>
