@@ -224,6 +224,9 @@ struct CullRect
 {
     // outward unit normals of the four side planes of the rect's ray frustum (apex = origin)
     float nl[3], nr[3], nb[3], nt[3];
+    // unit directions of the four corner rays (u0,v0) (u1,v0) (u0,v1) (u1,v1)
+    float e00[3], e10[3], e01[3], e11[3];
+    float c00, c10, c01, c11; // cosines between the adjacent planes' normals at those corners
     int tx0, tx1, ty0, ty1; // reference tile range covered
     bool exact_tile;        // single tile: evaluate the predicate exactly
 };
@@ -260,6 +263,18 @@ __device__ void make_rect(int x0, int x1, int y0, int y1, CullRect &rc)
     cross3(G.inv0, a, rc.nb); orient_normalize(rc.nb, G.inv1, -1.f);
     for (int i = 0; i < 3; ++i) a[i] = v1 * G.inv1[i] + Wv[i];
     cross3(G.inv0, a, rc.nt); orient_normalize(rc.nt, G.inv1, +1.f);
+    {
+        const float us[2] = {u0, u1}, vs[2] = {v0, v1};
+        float *es[4] = {rc.e00, rc.e10, rc.e01, rc.e11};
+        for (int c = 0; c < 4; ++c)
+        {
+            float *e = es[c];
+            for (int i = 0; i < 3; ++i) e[i] = us[c & 1] * G.inv0[i] + vs[c >> 1] * G.inv1[i] + Wv[i];
+            const float inv = rsqrtf(fmaxf(dot3(e, e), 1e-30f));
+            e[0] *= inv; e[1] *= inv; e[2] *= inv;
+        }
+    }
+    rc.c00 = dot3(rc.nl, rc.nb); rc.c10 = dot3(rc.nr, rc.nb); rc.c01 = dot3(rc.nl, rc.nt); rc.c11 = dot3(rc.nr, rc.nt);
     rc.tx0 = x0 / G.tile_w; rc.tx1 = (x1 - 1) / G.tile_w;
     rc.ty0 = y0 / G.tile_h; rc.ty1 = (y1 - 1) / G.tile_h;
     rc.exact_tile = (rc.tx0 == rc.tx1) && (rc.ty0 == rc.ty1);
@@ -295,10 +310,34 @@ __device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, co
         // distance budget: k sigma, plus the w offset can only increase the true distance (ignored => conservative)
         const float lim = G.bound_k * sigma + 1e-6f * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z));
         const float dl = dot3(p, rc.nl), dr = dot3(p, rc.nr), db = dot3(p, rc.nb), dt = dot3(p, rc.nt);
-        const bool front = dl <= lim && dr <= lim && db <= lim && dt <= lim;
+        // Inside the k-sigma slab of all four planes; a centre that is outside TWO adjacent planes is nearest to the corner
+        // ray, so its distance to that ray's line decides (rounded corners instead of a box: ~14 % shorter lists).
+        auto near_frustum = [&](float sl, float sr, float sb, float st) -> bool {
+            if (!(sl <= lim && sr <= lim && sb <= lim && st <= lim)) return false;
+            // outside two adjacent planes (distances su, sv > 0, cosine c between their normals): the corner ray is the
+            // nearest feature only if the centre projects beyond the edge on BOTH faces (su - sv c > 0 and sv - su c > 0);
+            // otherwise a face is nearest and its plane distance (already <= lim) is the true distance
+            const float *e = nullptr;
+            float su = 0.f, sv = 0.f, c = 0.f;
+            if (sb > 0.f)
+            {
+                if (sl > 0.f) { e = rc.e00; su = sl; sv = sb; c = rc.c00; }
+                else if (sr > 0.f) { e = rc.e10; su = sr; sv = sb; c = rc.c10; }
+            }
+            else if (st > 0.f)
+            {
+                if (sl > 0.f) { e = rc.e01; su = sl; sv = st; c = rc.c01; }
+                else if (sr > 0.f) { e = rc.e11; su = sr; sv = st; c = rc.c11; }
+            }
+            if (e == nullptr || !(su - sv * c > 0.f && sv - su * c > 0.f)) return true;
+            const float q = dot3(p, e);
+            const float px = p[0] - q * e[0], py = p[1] - q * e[1], pz = p[2] - q * e[2];
+            return px * px + py * py + pz * pz <= lim * lim;
+        };
+        const bool front = near_frustum(dl, dr, db, dt);
         // the reference integrates along the whole line (samples with s < 0 are not guarded, rt.h:155-160),
         // so the mirrored frustum counts too
-        const bool back = -dl <= lim && -dr <= lim && -db <= lim && -dt <= lim;
+        const bool back = near_frustum(-dl, -dr, -db, -dt);
         if (!(front || back)) return false;
     }
     return true;

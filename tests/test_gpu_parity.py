@@ -308,6 +308,44 @@ def test_bound_mode_matches_all(pkg, renderer):
     assert err_ref > err_gpu
 
 
+def test_bounded_lists_are_conservative_and_tight(pkg, renderer):
+    """K1's k-sigma bound per 8x4 cell: no Gaussian that comes within k sigma of ANY of the cell's 32 rays may be missing
+    (conservative), every member passes the four-plane box test of oracle/cpu_lists.py (never looser than the box), and the
+    corner refinement makes the lists measurably shorter than the box."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import cpu_lists
+
+    V = pkg.vrt
+    W, k = 256, 6.0
+    scene = pkg.scenes.synthetic(4000, 11, -1.9, -1.2)
+    for rotation in (0.0, 27.0):
+        cam, origin = V.camera_t.app(W, W, rotation=rotation)
+        renderer.set_gaussians(scene)
+        f = renderer.frame(cam.view_matrix, origin, W, W, (V.MODE4 & ~V.LIST_MASK) | V.LIST_BOUND, (1, 1), k)
+        renderer.tile(f)
+        counts, idx = renderer.get_lists()
+        ncx, ncy = W // 8, W // 4
+        assert len(counts) == ncx * ncy
+        offs = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+        rng = np.random.default_rng(3)
+        n_gpu = n_box = n_need = 0
+        for cell in rng.integers(0, ncx * ncy, 60):
+            cx, cy = int(cell) % ncx, int(cell) // ncx
+            got = set(idx[offs[cell] : offs[cell + 1]].tolist())
+            pix = np.array([(cy * 4 + r) * W + cx * 8 + c for r in range(4) for c in range(8)], np.uint64)
+            dirs = Oracle.pixel_dirs(cam.view_matrix, origin, W, W, pix)
+            need = set(np.nonzero((cpu_lists.ray_distance_sigmas(scene, origin, dirs) <= k * 0.999).any(1))[0].tolist())
+            planes = cpu_lists.rect_planes(cam.view_matrix, origin, W, W, cx * 8, cx * 8 + 8, cy * 4, cy * 4 + 4)
+            box = set(np.nonzero(cpu_lists.rect_bound_member(scene, origin, planes, k * 1.001))[0].tolist())
+            assert need <= got, (cell, sorted(need - got))
+            assert got <= box, (cell, sorted(got - box))
+            n_gpu, n_box, n_need = n_gpu + len(got), n_box + len(box), n_need + len(need)
+        print(f"rotation {rotation}: exact {n_need}, K1 {n_gpu}, four-plane box {n_box}")
+        assert n_gpu < 0.95 * n_box
+
+
 def test_errors_are_reported(pkg, renderer):
     V = pkg.vrt
     cam, origin = V.camera_t.app(100, 100)
