@@ -46,6 +46,7 @@ class Stats(ctypes.Structure):
         ("ms_render", c_f),
         ("ms_total", c_f),
         ("reserved", c_f),
+        ("terms_saturated", c_d),
     ]
 
     def as_dict(self):

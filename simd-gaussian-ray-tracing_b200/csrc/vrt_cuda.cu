@@ -473,6 +473,73 @@ __global__ void __launch_bounds__(256) k1_cull_tiles(const Rec *__restrict__ rec
     if (!WRITE && threadIdx.x == 0) counts[tile] = s_base;
 }
 
+// Depth order for the depth-window mode: every cell's index list is sorted by the depth of the centre along the cell's
+// centre ray (ties by Gaussian index, so the order is deterministic).  One warp per cell, bitonic network in shared memory;
+// lists longer than SORT_CAP stay in index order (the window test is valid for any order, it just saturates less often).
+constexpr int SORT_CAP = 512;
+__device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int &w, int &h);
+__global__ void __launch_bounds__(128) k1_sort_cells(const Rec *__restrict__ rec, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ list_idx,
+                                                     uint32_t n_cells)
+{
+    __shared__ float s_key[4][SORT_CAP];
+    __shared__ uint32_t s_val[4][SORT_CAP];
+    const FrameGeom &G = c_geom;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t cell = blockIdx.x * 4 + w;
+    if (cell >= n_cells) return;
+    const uint32_t off = list_off[cell], n = list_off[cell + 1] - off;
+    if (n < 2 || n > SORT_CAP) return;
+    int x0, y0, cw, ch;
+    cell_rect((int)(cell % G.ncx), (int)(cell / G.ncx), x0, y0, cw, ch);
+    // centre ray of the cell
+    const float u = -1.f + ((float)x0 + 0.5f * (float)(cw - 1)) / G.half_w, v = -1.f + ((float)y0 + 0.5f * (float)(ch - 1)) / G.half_h;
+    float d[3];
+    for (int i = 0; i < 3; ++i) d[i] = (G.inv0[i] * u + G.inv1[i] * v) + G.inv3[i] - G.origin[i];
+    const float inv = rsqrtf(fmaxf(dot3(d, d), 1e-30f));
+    uint32_t m = 2;
+    while (m < n) m <<= 1;
+    float *key = s_key[w];
+    uint32_t *val = s_val[w];
+    for (uint32_t i = lane; i < m; i += 32)
+    {
+        if (i < n)
+        {
+            const uint32_t gi = list_idx[off + i];
+            const float4 a = rec[gi].a;
+            key[i] = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
+            val[i] = gi;
+        }
+        else
+        {
+            key[i] = 3.0e38f;
+            val[i] = 0xFFFFFFFFu;
+        }
+    }
+    __syncwarp();
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1)
+        {
+            for (uint32_t i = lane; i < m; i += 32)
+            {
+                const uint32_t l = i ^ j;
+                if (l > i)
+                {
+                    const float ki = key[i], kl = key[l];
+                    const uint32_t vi = val[i], vl = val[l];
+                    const bool up = (i & k) == 0;
+                    const bool gt = ki > kl || (ki == kl && vi > vl);
+                    if (gt == up)
+                    {
+                        key[i] = kl; key[l] = ki;
+                        val[i] = vl; val[l] = vi;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    for (uint32_t i = lane; i < n; i += 32) list_idx[off + i] = val[i];
+}
+
 // exclusive scan of n counts into n+1 offsets; single CTA of 1024 threads (n <= a few million)
 __global__ void __launch_bounds__(1024) k1_scan(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n)
 {
@@ -508,6 +575,7 @@ struct TileStats
     unsigned long long max_list;
     double terms_listed;          // sum over band pixels of 5 n^2
     unsigned long long terms_exec; // filled by K2
+    unsigned long long terms_sat;  // K2, depth-window mode: terms resolved by saturation
 };
 
 __device__ __forceinline__ uint32_t cell_list_id(int cx, int cy)
@@ -631,8 +699,10 @@ struct RenderArgs
     uint32_t *image;           // W*H packed pixels (may be null)
     float4 *radiance;          // W*H float4 (may be null)
     unsigned long long *terms_exec;
+    unsigned long long *terms_sat;
     float skip_thresh;         // skip an occluder / emitter for the whole warp when exp2 weight <= thresh (-1: never)
     uint32_t quant_nearest, alpha_from_w;
+    uint32_t window; // depth-window mode
 };
 
 // ---- per-warp record staging -------------------------------------------------------------------------------------------
@@ -690,7 +760,7 @@ __device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, c
     e = ex2_approx(-d2 * b.y);
 }
 
-template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG>
+template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG, bool WIN>
 __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
 {
     __shared__ __align__(128) Rec s_rec[K2_WARPS][2][STAGE];
@@ -698,7 +768,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
     const FrameGeom &G = c_geom;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & (CELL_W - 1), ly = lane >> 3;
-    unsigned long long exec = 0;
+    unsigned long long exec = 0, sat = 0;
+    // depth window (WIN): erf saturates to +-esat beyond |t| >= tsat for both variants (A&S: 1 - 1/D^4 rounds to 1.0f from
+    // 5.45 on; the exact variant clamps |t| at 4), so an occluder that is that far in front of (behind) EVERY sample of the
+    // emitter block for EVERY lane contributes +A esat (-A esat) to all 5Q accumulators: one add instead of 5Q terms
+    const float tsat = ERF == 0 ? 5.5f : EX_XMAX;
+    const float esat = erf_variant<ERF>(tsat);
     uint32_t par = 0u; // phase parity of this warp's two mbarriers (bit b = buffer b)
     if (CONTIG && lane == 0)
     {
@@ -804,7 +879,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
             // emitter block
             float s[Q][5], acc[Q][5], wgt[Q];
             float4 alb[Q];
-            float s0 = 0.f;
+            float s0 = 0.f, smin = 3.0e38f, smax = -3.0e38f, base = 0.f;
             bool any_emit = false;
 #pragma unroll
             for (int e = 0; e < Q; ++e)
@@ -824,6 +899,11 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                 // emission weight sigma c_bar = Kl e / (sqrt(pi/2) log2e)
                 wgt[e] = real ? b.z * ee * (1.f / (SQRT_PI_2 * LOG2E)) : 0.f;
                 any_emit |= real && (ee > args.skip_thresh);
+                if (WIN && real)
+                {
+                    smin = fminf(smin, (mu - s0) - 4.f * b.w);
+                    smax = fmaxf(smax, mu - s0);
+                }
 #pragma unroll
                 for (int k = 0; k < 5; ++k)
                 {
@@ -898,6 +978,13 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                     const float A = b.z * e;
                     const float r = b.x;
                     const float nm = -(mu - s0) * r;
+                    if (WIN)
+                    {
+                        // t at the shallowest / deepest sample of the block for this lane
+                        const bool front = fmaf(smin, r, nm) >= tsat, back = fmaf(smax, r, nm) <= -tsat;
+                        if (__all_sync(0xffffffffu, front)) { base = fmaf(A, esat, base); sat += n_real; continue; }
+                        if (__all_sync(0xffffffffu, back)) { base = fmaf(-A, esat, base); sat += n_real; continue; }
+                    }
                     exec += n_real;
                     if (PACK)
                     {
@@ -933,11 +1020,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
 #pragma unroll
             for (int e = 0; e < Q; ++e)
             {
-                float inner = 3.3546262790251185e-4f * ex2_approx(C - acc[e][0]);
-                inner = fmaf(1.1108996538242306e-2f, ex2_approx(C - acc[e][1]), inner);
-                inner = fmaf(1.3533528323661270e-1f, ex2_approx(C - acc[e][2]), inner);
-                inner = fmaf(6.0653065971263342e-1f, ex2_approx(C - acc[e][3]), inner);
-                inner += ex2_approx(C - acc[e][4]);
+                const float Cb = WIN ? C - base : C;
+                float inner = 3.3546262790251185e-4f * ex2_approx(Cb - acc[e][0]);
+                inner = fmaf(1.1108996538242306e-2f, ex2_approx(Cb - acc[e][1]), inner);
+                inner = fmaf(1.3533528323661270e-1f, ex2_approx(Cb - acc[e][2]), inner);
+                inner = fmaf(6.0653065971263342e-1f, ex2_approx(Cb - acc[e][3]), inner);
+                inner += ex2_approx(Cb - acc[e][4]);
                 inner *= wgt[e];
                 Lr = fmaf(alb[e].x, inner, Lr);
                 Lg = fmaf(alb[e].y, inner, Lg);
@@ -968,11 +1056,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                 args.image[pi] = (A << 24) | (R << 16) | (Gc << 8) | B;
             }
         }
-        if (lane == 0 && exec)
-        {
-            atomicAdd(args.terms_exec, exec * 5ull * n_live);
-        }
+        if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
+        if (WIN && lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
         exec = 0;
+        sat = 0;
     }
 }
 
@@ -1092,6 +1179,7 @@ struct vrt_cuda_ctx
     // state of the last tile()
     bool have_lists = false;
     bool lists_from_host = false;
+    bool lists_sorted = false;
     FrameGeom geom{};
     uint32_t n_lists = 0;
     uint64_t n_entries = 0;
@@ -1280,15 +1368,15 @@ int build_queue(vrt_cuda_ctx *ctx)
     return 0;
 }
 
-template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG>
+template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG, bool WIN = false>
 void launch_k2c(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, JU, CONTIG>, K2_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, JU, CONTIG, WIN>, K2_WARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-    k2_render<ERF, Q, PACK, MINB, JU, CONTIG><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+    k2_render<ERF, Q, PACK, MINB, JU, CONTIG, WIN><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
 }
 
 template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1), int JU = 1>
@@ -1305,6 +1393,13 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     // sample chains per thread beats occupancy (tools/tune_k2.py); short lists waste less padding with Q = 4
     const int q = ctx->tune_q ? ctx->tune_q : ((ctx->n_lists && ctx->n_entries / ctx->n_lists >= 24) ? 8 : 4);
     const bool p = ctx->tune_pack != 0;
+    if (a.window)
+    {
+        // depth-window mode (sorted index lists): Q = 8 blocks span a short depth range, Q = 4 for short lists
+        if (q >= 8) launch_k2c<ERF, 8, true, 1, 1, false, true>(ctx, a);
+        else launch_k2c<ERF, 4, true, 2, 1, false, true>(ctx, a);
+        return 0;
+    }
     // experimental occupancy variants: pack = 2 / 3 -> packed math with >= 3 / 4 CTAs per SM (register cap 80 / 64)
     if (ctx->tune_pack >= 2)
     {
@@ -1622,6 +1717,13 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
             }
         }
     }
+    ctx->lists_sorted = false;
+    if (G.list_kind == 0 && (frame->flags & VRT_CUDA_DEPTH_WINDOW) && ctx->n_entries)
+    {
+        k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
+        ctx->launches++;
+        ctx->lists_sorted = true;
+    }
     CU(cudaGetLastError());
     if (int rc = build_queue(ctx)) return rc;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1750,12 +1852,14 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.image = image_dev;
     a.radiance = (float4 *)radiance_dev;
     a.terms_exec = &((TileStats *)ctx->stats.p)->terms_exec;
+    a.terms_sat = &((TileStats *)ctx->stats.p)->terms_sat;
+    a.window = ((frame->flags & VRT_CUDA_DEPTH_WINDOW) && a.list_idx != nullptr) ? 1u : 0u;
     const bool bounded = G.use_bound != 0;
     a.skip_thresh = (frame->flags & VRT_CUDA_NO_SKIP) ? -1.f : (bounded ? std::exp2(-0.5f * G.bound_k * G.bound_k * LOG2E) : 0.f);
     a.quant_nearest = (frame->flags & VRT_CUDA_QUANT_NEAREST) ? 1u : 0u;
     a.alpha_from_w = (frame->flags & VRT_CUDA_ALPHA_FROM_W) ? 1u : 0u;
     CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));
-    CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_exec, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_exec, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     int rc = ((frame->flags & VRT_CUDA_ERF_MASK) == VRT_CUDA_ERF_EXACT) ? dispatch_k2<1>(ctx, a) : dispatch_k2<0>(ctx, a);
     if (rc) return rc;
@@ -1774,6 +1878,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         stats->n_launches = ctx->launches + 1;
         stats->terms_listed = ts.terms_listed;
         stats->terms_executed = (double)ts.terms_exec;
+        stats->terms_saturated = (double)ts.terms_sat;
         stats->ms_tile = ctx->ms_tile;
         CU(cudaEventElapsedTime(&stats->ms_render, ctx->ev[2], ctx->ev[3]));
         stats->ms_total = stats->ms_tile + stats->ms_render;

@@ -24,6 +24,7 @@ LIST_REFERENCE, LIST_REFERENCE_BOUND, LIST_ALL, LIST_BOUND = 0 << 2, 1 << 2, 2 <
 QUANT_TRUNCATE, QUANT_NEAREST = 0 << 4, 1 << 4
 ALPHA_OPAQUE, ALPHA_FROM_W = 0 << 5, 1 << 5
 NO_SKIP = 1 << 6
+DEPTH_WINDOW = 1 << 7
 MODE1 = ERF_EXACT | LIST_ALL | QUANT_TRUNCATE | ALPHA_OPAQUE
 MODE4 = ERF_AS | LIST_ALL | QUANT_NEAREST | ALPHA_OPAQUE
 MODE5 = ERF_EXACT | LIST_REFERENCE | QUANT_TRUNCATE | ALPHA_OPAQUE

@@ -346,6 +346,36 @@ def test_bounded_lists_are_conservative_and_tight(pkg, renderer):
         assert n_gpu < 0.95 * n_box
 
 
+@pytest.mark.parametrize("erf", [0, 1])
+def test_depth_window_mode_is_the_same_image(pkg, renderer, erf):
+    """VRT_CUDA_DEPTH_WINDOW: depth-sorted lists + the saturation shortcut must reproduce the plain evaluation (only the order
+    of the fp32 sums changes) while evaluating far fewer terms; every listed term is either evaluated or resolved."""
+    V = pkg.vrt
+    W = 512
+    scene = pkg.scenes.synthetic(60000, 21, -2.3, -1.7)
+    cam, origin = V.camera_t.app(W, W, rotation=12.0)
+    renderer.set_gaussians(scene)
+    base_flags = ((V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND) & ~1 | erf
+    f0 = renderer.frame(cam.view_matrix, origin, W, W, base_flags, (32, 32), 6.0)
+    img0, rad0, st0 = renderer.frame_render(f0, True, True)
+    f1 = renderer.frame(cam.view_matrix, origin, W, W, base_flags | V.DEPTH_WINDOW, (32, 32), 6.0)
+    img1, rad1, st1 = renderer.frame_render(f1, True, True)
+    d = float(np.abs(rad0 - rad1).max())
+    print(f"erf {erf}: plain {st0['terms_executed']:.3e} terms in {st0['ms_render']:.2f} ms; window {st1['terms_executed']:.3e} evaluated + "
+          f"{st1['terms_saturated']:.3e} saturated in {st1['ms_render']:.2f} ms; max |diff| {d:.2e}")
+    assert d <= 2e-5  # the saturated part enters as one large partial sum: fp32 reassociation ~ sum(A) * 2^-23
+    assert channel_diff_lsb(img0, img1) <= 1
+    assert st1["terms_listed"] == st0["terms_listed"]
+    # (emitter blocks group different emitters once the list is depth-sorted, so the warp-uniform skips differ marginally)
+    assert abs(st1["terms_executed"] + st1["terms_saturated"] - st0["terms_executed"]) <= 1e-3 * st0["terms_executed"]
+    assert st1["terms_executed"] < 0.5 * st0["terms_executed"]
+    assert st0["terms_saturated"] == 0
+    # and against the arbiter
+    pix = all_pixels(W, W, 997)
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1 - erf, f64="unit", near_sigmas=12)
+    check(gpu_at(rad1, pix, W), ideal, f"depth-window mode vs arbiter (erf {erf})")
+
+
 def test_errors_are_reported(pkg, renderer):
     V = pkg.vrt
     cam, origin = V.camera_t.app(100, 100)

@@ -23,10 +23,12 @@ def main():
         ("grid64_ref_noskip_band32", lambda: pkg.scenes.grid(64), 2048, (V.MODE8 | V.NO_SKIP), (16, 16), (1024, 1056)),
         ("config4_bound", pkg.scenes.config4, 4096, bound, (256, 256), (0, 0)),
         ("config5_bound", pkg.scenes.config5, 4096, bound, (256, 256), (0, 0)),
+        ("config5_window", pkg.scenes.config5, 4096, bound | V.DEPTH_WINDOW, (256, 256), (0, 0)),
+        ("config4_window", pkg.scenes.config4, 4096, bound | V.DEPTH_WINDOW, (256, 256), (0, 0)),
     ]
     variants = [(4, 1), (4, 2), (2, 1), (2, 2), (2, 3), (6, 1), (8, 1), (4, 0)]
     if quick:
-        variants = [(8, 1), (4, 1), (4, 4), (2, 4), (6, 4)]
+        variants = [(8, 1), (4, 1)]
     for name, scene_fn, W, flags, tiles, rows in work:
         if only and name != only:
             continue
@@ -50,7 +52,7 @@ def main():
                 rate = best["terms_executed"] / (best["ms_render"] * 1e-3)
                 rec = dict(work=name, erf=int(erf), q=q, pack=pack, ms_render=best["ms_render"], ms_tile=best["ms_tile"],
                            terms_executed=best["terms_executed"], terms_listed=best["terms_listed"], rate=rate,
-                           frac=rate * 15 / 74.45e12, max_list=best["max_list"], list_entries=best["list_entries"], host_tile_s=t_tile)
+                           frac=rate * 15 / 74.45e12, terms_saturated=best["terms_saturated"], max_list=best["max_list"], list_entries=best["list_entries"], host_tile_s=t_tile)
                 results.append(rec)
                 print(json.dumps(rec), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
