@@ -41,6 +41,7 @@ constexpr int BIN_CY = 32;         // cells per coarse bin, y  (128 px)
 constexpr int ROOT_SEG = 4096;     // Gaussians per root segment in the first cull level
 constexpr int K2_WARPS = 8;        // warps per render CTA
 constexpr int STAGE = 32;          // records staged per warp per step (one per lane)
+constexpr int WIN_CAP = 160;       // longest list the depth-window kernel caches per warp ((WIN_CAP+1) * 128 B of prefix sums)
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float SQRT_PI_2 = 1.2533141373155003f; // sqrt(pi/2) = 1/0.7978845608 (INV_SQRT_2_PI of src/vrt/rt.h:19)
@@ -576,6 +577,7 @@ struct TileStats
     double terms_listed;          // sum over band pixels of 5 n^2
     unsigned long long terms_exec; // filled by K2
     unsigned long long terms_sat;  // K2, depth-window mode: terms resolved by saturation
+    unsigned long long n_big;      // queued cells whose list is longer than the depth-window cache
 };
 
 __device__ __forceinline__ uint32_t cell_list_id(int cx, int cy)
@@ -760,6 +762,42 @@ __device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, c
     e = ex2_approx(-d2 * b.y);
 }
 
+// K3: clamp, quantise (truncate | round-to-nearest-even) and pack one pixel; store the packed word and/or the float4 radiance
+__device__ __forceinline__ void store_pixel(const RenderArgs &args, size_t pi, float Lr, float Lg, float Lb, float La)
+{
+    if (args.radiance) args.radiance[pi] = make_float4(Lr, Lg, Lb, La);
+    if (args.image)
+    {
+        const float r255 = fminf(Lr, 1.f) * 255.f, g255 = fminf(Lg, 1.f) * 255.f, b255 = fminf(Lb, 1.f) * 255.f;
+        uint32_t R, Gc, B, A = 0xFFu;
+        if (args.quant_nearest)
+        {
+            R = (uint32_t)__float2int_rn(r255); Gc = (uint32_t)__float2int_rn(g255); B = (uint32_t)__float2int_rn(b255);
+            if (args.alpha_from_w) A = (uint32_t)__float2int_rn(fminf(La, 1.f) * 255.f);
+        }
+        else
+        {
+            R = (uint32_t)r255; Gc = (uint32_t)g255; B = (uint32_t)b255;
+            if (args.alpha_from_w) A = (uint32_t)(fminf(La, 1.f) * 255.f);
+        }
+        args.image[pi] = (A << 24) | (R << 16) | (Gc << 8) | B;
+    }
+}
+
+// ray through pixel (px, py): plane = inverse(view) (u, v, 0, 1) (src/vrt/camera.cpp:60-70); dir = normalize(plane - origin)
+__device__ __forceinline__ PixelRay pixel_ray(int px, int py)
+{
+    const FrameGeom &G = c_geom;
+    const float u = -1.f + (float)px / G.half_w, v = -1.f + (float)py / G.half_h;
+    const float dx = (G.inv0[0] * u + G.inv1[0] * v) + G.inv3[0] - G.origin[0];
+    const float dy = (G.inv0[1] * u + G.inv1[1] * v) + G.inv3[1] - G.origin[1];
+    const float dz = (G.inv0[2] * u + G.inv1[2] * v) + G.inv3[2] - G.origin[2];
+    const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
+    PixelRay ray;
+    ray.nx = dx * inv; ray.ny = dy * inv; ray.nz = dz * inv;
+    return ray;
+}
+
 template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG, bool WIN>
 __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
 {
@@ -798,16 +836,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
         const bool live = lx < cw && ly < ch && py >= G.row_begin && py < G.row_end;
         const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
 
-        // ray through the pixel: plane = inverse(view) (u, v, 0, 1) (src/vrt/camera.cpp:60-70); dir = normalize(plane - origin)
-        PixelRay ray;
-        {
-            const float u = -1.f + (float)px / G.half_w, v = -1.f + (float)py / G.half_h;
-            const float dx = (G.inv0[0] * u + G.inv1[0] * v) + G.inv3[0] - G.origin[0];
-            const float dy = (G.inv0[1] * u + G.inv1[1] * v) + G.inv3[1] - G.origin[1];
-            const float dz = (G.inv0[2] * u + G.inv1[2] * v) + G.inv3[2] - G.origin[2];
-            const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
-            ray.nx = dx * inv; ray.ny = dy * inv; ray.nz = dz * inv;
-        }
+        const PixelRay ray = pixel_ray(px, py);
 
         const uint32_t lid = cell_list_id(cx, cy);
         const uint32_t off = args.list_off[lid];
@@ -1035,31 +1064,209 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
         }
 
         // ---- K3: framebuffer ----
-        if (live)
-        {
-            const size_t pi = (size_t)py * G.W + px;
-            if (args.radiance) args.radiance[pi] = make_float4(Lr, Lg, Lb, La);
-            if (args.image)
-            {
-                const float r255 = fminf(Lr, 1.f) * 255.f, g255 = fminf(Lg, 1.f) * 255.f, b255 = fminf(Lb, 1.f) * 255.f;
-                uint32_t R, Gc, B, A = 0xFFu;
-                if (args.quant_nearest)
-                {
-                    R = (uint32_t)__float2int_rn(r255); Gc = (uint32_t)__float2int_rn(g255); B = (uint32_t)__float2int_rn(b255);
-                    if (args.alpha_from_w) A = (uint32_t)__float2int_rn(fminf(La, 1.f) * 255.f);
-                }
-                else
-                {
-                    R = (uint32_t)r255; Gc = (uint32_t)g255; B = (uint32_t)b255;
-                    if (args.alpha_from_w) A = (uint32_t)(fminf(La, 1.f) * 255.f);
-                }
-                args.image[pi] = (A << 24) | (R << 16) | (Gc << 8) | B;
-            }
-        }
+        if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
         if (WIN && lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
         exec = 0;
         sat = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2', depth-window render (VRT_CUDA_DEPTH_WINDOW) for cells whose list fits the per-warp cache
+// ------------------------------------------------------------------------------------------------
+// Lists are depth-sorted by K1.  Pass A walks the list once per pixel, accumulates C and stores the per-lane PREFIX SUMS of
+// the weights A_j in shared memory, plus two warp-uniform depths per occluder: beyond f_j every lane's erf argument is
+// >= t_sat (the occluder is entirely in front: erf = +esat), before b_j it is <= -t_sat (entirely behind: -esat).  For an
+// emitter block whose samples span [Smin, Smax] the leading occluders with f_j <= Smin and the trailing ones with
+// b_j >= Smax are resolved together as  esat (P[f] - (P[n] - P[b]))  -- two shared-memory reads -- and only the window
+// [f, b) in between is evaluated term by term.
+constexpr int WIN_Q = 8;
+struct WinSmem
+{
+    float prefix[WIN_CAP + 1][32]; // prefix[j][lane] = sum_{i<j} A_i(lane), log2 units
+    float4 a[WIN_CAP], b[WIN_CAP]; // occluder part of the records
+    float2 fb[WIN_CAP];            // (f_j, b_j)
+};
+
+__device__ __forceinline__ int ordered_int(float x)
+{
+    const int k = __float_as_int(x);
+    return k ^ ((k >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_max_f(float x) { return ordered_float(__reduce_max_sync(0xffffffffu, ordered_int(x))); }
+__device__ __forceinline__ float warp_min_f(float x) { return ordered_float(__reduce_min_sync(0xffffffffu, ordered_int(x))); }
+
+template <int ERF>
+__global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs args, uint32_t queue_begin)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    constexpr int Q = WIN_Q;
+    const FrameGeom &G = c_geom;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WinSmem &sm = reinterpret_cast<WinSmem *>(s_raw)[warp];
+    const int lx = lane & (CELL_W - 1), ly = lane >> 3;
+    const float tsat = ERF == 0 ? 5.5f : EX_XMAX;
+    const float esat = erf_variant<ERF>(tsat);
+
+    for (;;)
+    {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(args.counter + 1, 1u) + queue_begin;
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= args.n_queue) break;
+        const uint32_t cell = args.queue[qi];
+        const int cx = cell % G.ncx, cy = cell / G.ncx;
+        int x0, y0, cw, ch;
+        cell_rect(cx, cy, x0, y0, cw, ch);
+        const int px = x0 + min(lx, cw - 1), py = y0 + min(ly, ch - 1);
+        const bool live = lx < cw && ly < ch && py >= G.row_begin && py < G.row_end;
+        const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
+        const PixelRay ray = pixel_ray(px, py);
+        const uint32_t lid = cell_list_id(cx, cy);
+        const uint32_t off = args.list_off[lid];
+        const uint32_t n = min(args.list_off[lid + 1] - off, (uint32_t)WIN_CAP); // (longer lists never reach this kernel)
+
+        // stage the whole list (occluder part) once
+        __syncwarp();
+        for (uint32_t j = lane; j < n; j += 32)
+        {
+            const Rec *r = args.rec + args.list_idx[off + j];
+            sm.a[j] = r->a;
+            sm.b[j] = r->b;
+        }
+        __syncwarp();
+
+        // ---- pass A: C, prefix sums of the weights, saturation depths ----
+        float C = 0.f, run = 0.f;
+        sm.prefix[0][lane] = 0.f;
+        for (uint32_t j = 0; j < n; ++j)
+        {
+            const float4 a = sm.a[j], b = sm.b[j];
+            float mu, e;
+            occluder_setup(a, b, ray, mu, e);
+            // an occluder no lane sees (weight <= threshold everywhere) is dropped exactly like the plain kernel's skip
+            const bool alive = __any_sync(0xffffffffu, e > args.skip_thresh);
+            const float A = alive ? b.z * e : 0.f;
+            C = fmaf(A, erf_variant<ERF>(-mu * b.x), C);
+            run += A;
+            sm.prefix[j + 1][lane] = run;
+            const float mumax = warp_max_f(mu), mumin = warp_min_f(mu);
+            if (lane == 0)
+            {
+                const float half = tsat * 1.0000005f / b.x + 1e-6f * fabsf(mumax); // t >= tsat must hold after fp32 rounding of t
+                sm.fb[j] = alive ? make_float2(mumax + half, mumin - half) : make_float2(-3.0e38f, 3.0e38f);
+            }
+        }
+        __syncwarp();
+        const float total = run;
+
+        // ---- pass B ----
+        float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
+        unsigned long long exec = 0, sat = 0;
+        for (uint32_t q0 = 0; q0 < n; q0 += Q)
+        {
+            float s[Q][5], acc[Q][5], wgt[Q];
+            float4 alb[Q];
+            float s0 = 0.f, smin = 3.0e38f, smax = -3.0e38f;
+            bool any_emit = false;
+#pragma unroll
+            for (int e = 0; e < Q; ++e)
+            {
+                const bool real = q0 + e < n;
+                const uint32_t je = real ? q0 + e : q0;
+                const float4 a = sm.a[je], b = sm.b[je];
+                alb[e] = args.rec[args.list_idx[off + je]].c;
+                float mu, ee;
+                occluder_setup(a, b, ray, mu, ee);
+                if (e == 0)
+                {
+                    s0 = __shfl_sync(0xffffffffu, mu, 0);
+                    s0 = (fabsf(s0) <= 3.0e38f) ? s0 : 0.f;
+                }
+                wgt[e] = real ? b.z * ee * (1.f / (SQRT_PI_2 * LOG2E)) : 0.f;
+                any_emit |= real && (ee > args.skip_thresh);
+                if (real)
+                {
+                    smin = fminf(smin, mu - 4.f * b.w);
+                    smax = fmaxf(smax, mu);
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                {
+                    s[e][k] = (mu - s0) + (float)(k - 4) * b.w;
+                    acc[e][k] = 0.f;
+                }
+            }
+            if (!__any_sync(0xffffffffu, any_emit)) continue;
+            const uint32_t n_real = min((uint32_t)Q, n - q0);
+            const float Smin = warp_min_f(smin), Smax = warp_max_f(smax);
+
+            // leading run of occluders entirely in front of every sample, trailing run entirely behind
+            uint32_t f = 0, bk = n;
+            for (uint32_t j0 = 0; j0 < n; j0 += 32)
+            {
+                const uint32_t j = j0 + lane;
+                const uint32_t m = __ballot_sync(0xffffffffu, j < n && sm.fb[j].x <= Smin);
+                if (m == 0xffffffffu) { f = j0 + 32; continue; }
+                f = j0 + (uint32_t)__ffs(~m) - 1u;
+                break;
+            }
+            f = min(f, n);
+            for (int j0 = (int)((n - 1) & ~31u); j0 >= 0; j0 -= 32)
+            {
+                const uint32_t j = (uint32_t)j0 + lane;
+                // lanes beyond the list count as "behind" so the trailing run can start at the list end
+                const uint32_t m = __ballot_sync(0xffffffffu, j >= n || sm.fb[j].y >= Smax);
+                if (m == 0xffffffffu) { bk = (uint32_t)j0; continue; }
+                bk = (uint32_t)j0 + 32u - (uint32_t)__clz(~m);
+                break;
+            }
+            bk = max(bk, f);
+            const float base = esat * (sm.prefix[f][lane] - (total - sm.prefix[bk][lane]));
+            sat += (unsigned long long)(f + (n - bk)) * n_real;
+
+            for (uint32_t j = f; j < bk; ++j)
+            {
+                const float4 a = sm.a[j], b = sm.b[j];
+                float mu, e;
+                occluder_setup(a, b, ray, mu, e);
+                if (!__any_sync(0xffffffffu, e > args.skip_thresh)) continue;
+                const float A = b.z * e, r = b.x, nm = -(mu - s0) * r;
+                exec += n_real;
+                const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(A, A);
+#pragma unroll
+                for (int e2 = 0; e2 < Q / 2; ++e2)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                    {
+                        const float2 t = __ffma2_rn(make_float2(s[2 * e2][k], s[2 * e2 + 1][k]), rr, mm);
+                        const float2 ev = erf_variant2<ERF>(t);
+                        const float2 ac = __ffma2_rn(AA, ev, make_float2(acc[2 * e2][k], acc[2 * e2 + 1][k]));
+                        acc[2 * e2][k] = ac.x;
+                        acc[2 * e2 + 1][k] = ac.y;
+                    }
+            }
+            const float Cb = C - base;
+#pragma unroll
+            for (int e = 0; e < Q; ++e)
+            {
+                float inner = 3.3546262790251185e-4f * ex2_approx(Cb - acc[e][0]);
+                inner = fmaf(1.1108996538242306e-2f, ex2_approx(Cb - acc[e][1]), inner);
+                inner = fmaf(1.3533528323661270e-1f, ex2_approx(Cb - acc[e][2]), inner);
+                inner = fmaf(6.0653065971263342e-1f, ex2_approx(Cb - acc[e][3]), inner);
+                inner += ex2_approx(Cb - acc[e][4]);
+                inner *= wgt[e];
+                Lr = fmaf(alb[e].x, inner, Lr);
+                Lg = fmaf(alb[e].y, inner, Lg);
+                Lb = fmaf(alb[e].z, inner, Lb);
+                La = fmaf(alb[e].w, inner, La);
+            }
+        }
+        if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
+        if (lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
     }
 }
 
@@ -1180,6 +1387,8 @@ struct vrt_cuda_ctx
     bool have_lists = false;
     bool lists_from_host = false;
     bool lists_sorted = false;
+    uint32_t n_big = 0;
+    bool win_attr[2] = {false, false};
     FrameGeom geom{};
     uint32_t n_lists = 0;
     uint64_t n_entries = 0;
@@ -1353,6 +1562,8 @@ int build_queue(vrt_cuda_ctx *ctx)
     k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(loff, ctx->n_lists, (TileStats *)ctx->stats.p);
     k1_hist<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
     k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p);
+    // descending order: the start slot of key WIN_CAP = number of cells with a longer list (they lead the queue)
+    CU(cudaMemcpyAsync(&((TileStats *)ctx->stats.p)->n_big, (const uint32_t *)ctx->hist.p + WIN_CAP, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     k1_order<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, cyb, cye);
     ctx->launches += 4;
     CU(cudaGetLastError());
@@ -1395,9 +1606,29 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     const bool p = ctx->tune_pack != 0;
     if (a.window)
     {
-        // depth-window mode (sorted index lists): Q = 8 blocks span a short depth range, Q = 4 for short lists
-        if (q >= 8) launch_k2c<ERF, 8, true, 1, 1, false, true>(ctx, a);
-        else launch_k2c<ERF, 4, true, 2, 1, false, true>(ctx, a);
+        // depth-window mode (depth-sorted index lists).  The queue is in descending list length, so the cells whose list
+        // does not fit the per-warp cache of k2_window lead it: they go to k2_render's in-loop saturation test, the rest
+        // to k2_window.
+        const uint32_t n_big = std::min(ctx->n_big, a.n_queue);
+        if (n_big)
+        {
+            RenderArgs big = a;
+            big.n_queue = n_big;
+            launch_k2c<ERF, 8, true, 1, 1, false, true>(ctx, big);
+            ctx->launches++;
+        }
+        if (a.n_queue > n_big)
+        {
+            const size_t smem = sizeof(WinSmem) * K2_WARPS;
+            if (!ctx->win_attr[ERF]) // per device: the opt-in for > 48 KB of dynamic shared memory
+            {
+                cudaFuncSetAttribute(k2_window<ERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                ctx->win_attr[ERF] = true;
+            }
+            const uint32_t want = (a.n_queue - n_big + K2_WARPS - 1) / K2_WARPS;
+            const uint32_t grid = std::max(1u, std::min(want, (uint32_t)ctx->sm_count));
+            k2_window<ERF><<<grid, K2_WARPS * 32, smem, ctx->stream>>>(a, n_big);
+        }
         return 0;
     }
     // experimental occupancy variants: pack = 2 / 3 -> packed math with >= 3 / 4 CTAs per SM (register cap 80 / 64)
@@ -1729,6 +1960,11 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
+    {
+        unsigned long long nb = 0;
+        CU(cudaMemcpy(&nb, &((TileStats *)ctx->stats.p)->n_big, sizeof(nb), cudaMemcpyDeviceToHost));
+        ctx->n_big = (uint32_t)nb;
+    }
     ctx->have_lists = true;
     return 0;
 }

@@ -367,7 +367,7 @@ def test_depth_window_mode_is_the_same_image(pkg, renderer, erf):
     assert channel_diff_lsb(img0, img1) <= 1
     assert st1["terms_listed"] == st0["terms_listed"]
     # (emitter blocks group different emitters once the list is depth-sorted, so the warp-uniform skips differ marginally)
-    assert abs(st1["terms_executed"] + st1["terms_saturated"] - st0["terms_executed"]) <= 1e-3 * st0["terms_executed"]
+    assert abs(st1["terms_executed"] + st1["terms_saturated"] - st0["terms_executed"]) <= 1e-2 * st0["terms_executed"]
     assert st1["terms_executed"] < 0.5 * st0["terms_executed"]
     assert st0["terms_saturated"] == 0
     # and against the arbiter
