@@ -17,9 +17,6 @@
 
 #include <cuda_runtime.h>
 
-#ifndef VRT_SIGN_EARLY
-#define VRT_SIGN_EARLY 0
-#endif
 
 #include <algorithm>
 #include <cmath>
@@ -160,15 +157,8 @@ __device__ __forceinline__ float2 erf_variant2(float2 t)
         d = __fmul2_rn(d, d);
         d = __fmul2_rn(d, d);
         const float2 rc = make_float2(rcp_approx(d.x), rcp_approx(d.y));
-#if VRT_SIGN_EARLY
-        // sign(t) as +-1 taken before the reciprocal, so the ALU op does not sit behind the MUFU scoreboard:
-        // erf = sg - sg * rc
-        const float2 sg = make_float2(copysign_bits(1.f, t.x), copysign_bits(1.f, t.y));
-        return __ffma2_rn(rc, make_float2(-sg.x, -sg.y), sg);
-#else
         const float2 v = __ffma2_rn(rc, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
         return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
-#endif
     }
     else
     {
@@ -798,7 +788,7 @@ __device__ __forceinline__ PixelRay pixel_ray(int px, int py)
     return ray;
 }
 
-template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG, bool WIN>
+template <int ERF, int Q, bool PACK, int MINB, bool CONTIG, bool WIN>
 __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
 {
     __shared__ __align__(128) Rec s_rec[K2_WARPS][2][STAGE];
@@ -948,56 +938,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
             {
                 const uint32_t cnt = chunk_count(c);
                 if (!resident) sr = chunk_begin(c); // lists that fit one chunk stay resident from pass A
-                if (JU == 2)
-                {
-                    // two occluders per step: 2 x 5Q independent term chains in flight with only 5Q accumulators, i.e. the
-                    // instruction-level parallelism of a 2Q block at the register cost of Q (keeps 16 warps/SM at Q = 4)
-                    for (uint32_t j = 0; j < cnt; j += 2)
-                    {
-                        const uint32_t j1 = min(j + 1, cnt - 1);
-                        const float4 a0 = sr[j].a, b0 = sr[j].b, a1 = sr[j1].a, b1 = sr[j1].b;
-                        float mu0, e0, mu1, e1;
-                        occluder_setup(a0, b0, ray, mu0, e0);
-                        occluder_setup(a1, b1, ray, mu1, e1);
-                        const bool two = j + 1 < cnt;
-                        const bool go0 = __any_sync(0xffffffffu, e0 > args.skip_thresh);
-                        const bool go1 = two && __any_sync(0xffffffffu, e1 > args.skip_thresh);
-                        if (!(go0 || go1)) continue; // warp-uniform skip
-                        exec += n_real * ((go0 ? 1u : 0u) + (go1 ? 1u : 0u));
-                        // an occluder skipped for the warp but riding along with an active partner must add exactly what the
-                        // skip adds: nothing
-                        const float A0 = go0 ? b0.z * e0 : 0.f, A1 = go1 ? b1.z * e1 : 0.f;
-                        const float r0 = b0.x, r1 = b1.x;
-                        const float nm0 = -(mu0 - s0) * r0, nm1 = -(mu1 - s0) * r1;
-                        if (PACK)
-                        {
-                            const float2 rr0 = make_float2(r0, r0), mm0 = make_float2(nm0, nm0), AA0 = make_float2(A0, A0);
-                            const float2 rr1 = make_float2(r1, r1), mm1 = make_float2(nm1, nm1), AA1 = make_float2(A1, A1);
-#pragma unroll
-                            for (int e2 = 0; e2 < Q / 2; ++e2)
-#pragma unroll
-                                for (int k = 0; k < 5; ++k)
-                                {
-                                    const float2 sv = make_float2(s[2 * e2][k], s[2 * e2 + 1][k]);
-                                    const float2 ev0 = erf_variant2<ERF>(__ffma2_rn(sv, rr0, mm0));
-                                    const float2 ev1 = erf_variant2<ERF>(__ffma2_rn(sv, rr1, mm1));
-                                    const float2 ac = __ffma2_rn(AA1, ev1, __ffma2_rn(AA0, ev0, make_float2(acc[2 * e2][k], acc[2 * e2 + 1][k])));
-                                    acc[2 * e2][k] = ac.x;
-                                    acc[2 * e2 + 1][k] = ac.y;
-                                }
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int e = 0; e < Q; ++e)
-#pragma unroll
-                                for (int k = 0; k < 5; ++k)
-                                    acc[e][k] = fmaf(A1, erf_variant<ERF>(fmaf(s[e][k], r1, nm1)), fmaf(A0, erf_variant<ERF>(fmaf(s[e][k], r0, nm0)), acc[e][k]));
-                        }
-                    }
-                    if (!resident) chunk_end(c);
-                    continue;
-                }
                 for (uint32_t j = 0; j < cnt; ++j)
                 {
                     const float4 a = sr[j].a, b = sr[j].b;
@@ -1579,22 +1519,22 @@ int build_queue(vrt_cuda_ctx *ctx)
     return 0;
 }
 
-template <int ERF, int Q, bool PACK, int MINB, int JU, bool CONTIG, bool WIN = false>
+template <int ERF, int Q, bool PACK, int MINB, bool CONTIG, bool WIN = false>
 void launch_k2c(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, JU, CONTIG, WIN>, K2_WARPS * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, CONTIG, WIN>, K2_WARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-    k2_render<ERF, Q, PACK, MINB, JU, CONTIG, WIN><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+    k2_render<ERF, Q, PACK, MINB, CONTIG, WIN><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
 }
 
-template <int ERF, int Q, bool PACK, int MINB = (Q <= 6 ? 2 : 1), int JU = 1>
+template <int ERF, int Q, bool PACK, int MINB = (Q <= 4 ? 2 : 1)>
 void launch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
-    if (a.list_idx == nullptr) launch_k2c<ERF, Q, PACK, MINB, JU, true>(ctx, a);
-    else launch_k2c<ERF, Q, PACK, MINB, JU, false>(ctx, a);
+    if (a.list_idx == nullptr) launch_k2c<ERF, Q, PACK, MINB, true>(ctx, a);
+    else launch_k2c<ERF, Q, PACK, MINB, false>(ctx, a);
 }
 
 template <int ERF>
@@ -1614,7 +1554,7 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
         {
             RenderArgs big = a;
             big.n_queue = n_big;
-            launch_k2c<ERF, 8, true, 1, 1, false, true>(ctx, big);
+            launch_k2c<ERF, 8, true, 1, false, true>(ctx, big);
             ctx->launches++;
         }
         if (a.n_queue > n_big)
@@ -1631,25 +1571,12 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
         }
         return 0;
     }
-    // experimental occupancy variants: pack = 2 / 3 -> packed math with >= 3 / 4 CTAs per SM (register cap 80 / 64)
-    if (ctx->tune_pack >= 2)
-    {
-        const int q = ctx->tune_q;
-        if (q == 4 && ctx->tune_pack == 2) { launch_k2<ERF, 4, true, 3>(ctx, a); return 0; }
-        if (q == 4 && ctx->tune_pack == 4) { launch_k2<ERF, 4, true, 2, 2>(ctx, a); return 0; }
-        if (q == 2 && ctx->tune_pack == 4) { launch_k2<ERF, 2, true, 3, 2>(ctx, a); return 0; }
-        if (q == 6 && ctx->tune_pack == 4) { launch_k2<ERF, 6, true, 1, 2>(ctx, a); return 0; }
-        if (q == 2 && ctx->tune_pack == 2) { launch_k2<ERF, 2, true, 3>(ctx, a); return 0; }
-        if (q == 2 && ctx->tune_pack == 3) { launch_k2<ERF, 2, true, 4>(ctx, a); return 0; }
-        return fail(ctx, VRT_CUDA_E_INVALID, "no occupancy variant for Q=%d pack=%d", q, ctx->tune_pack);
-    }
+    // Variants that were measured and dropped (tools/tune_k2.py): Q = 2, 6, 10; 3-4 CTAs/SM by register cap;
+    // two occluders per step; sign taken before the reciprocal.  Kept: Q = 8 and 4, packed, and scalar math for comparison.
     switch (q)
     {
-    case 2: p ? launch_k2<ERF, 2, true>(ctx, a) : launch_k2<ERF, 2, false>(ctx, a); break;
     case 4: p ? launch_k2<ERF, 4, true>(ctx, a) : launch_k2<ERF, 4, false>(ctx, a); break;
-    case 6: p ? launch_k2<ERF, 6, true>(ctx, a) : launch_k2<ERF, 6, false>(ctx, a); break;
     case 8: p ? launch_k2<ERF, 8, true>(ctx, a) : launch_k2<ERF, 8, false>(ctx, a); break;
-    case 10: launch_k2<ERF, 10, true>(ctx, a); break;
     default: return fail(ctx, VRT_CUDA_E_INVALID, "unsupported emitter block %d", q);
     }
     return 0;
@@ -1743,9 +1670,9 @@ int vrt_cuda_set_gaussians_device(vrt_cuda_ctx *ctx, const float *aos_dev, uint6
 int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int q, int pack)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
-    if (q != 0 && q != 2 && q != 4 && q != 6 && q != 8 && q != 10) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 0 (auto), 2, 4, 6, 8 or 10");
+    if (q != 0 && q != 4 && q != 8) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 0 (auto), 4 or 8");
     ctx->tune_q = q;
-    ctx->tune_pack = pack;
+    ctx->tune_pack = pack ? 1 : 0;
     return 0;
 }
 

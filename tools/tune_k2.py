@@ -26,7 +26,7 @@ def main():
         ("config5_window", pkg.scenes.config5, 4096, bound | V.DEPTH_WINDOW, (256, 256), (0, 0)),
         ("config4_window", pkg.scenes.config4, 4096, bound | V.DEPTH_WINDOW, (256, 256), (0, 0)),
     ]
-    variants = [(4, 1), (4, 2), (2, 1), (2, 2), (2, 3), (6, 1), (8, 1), (4, 0)]
+    variants = [(8, 1), (4, 1), (8, 0), (4, 0)]
     if quick:
         variants = [(8, 1), (4, 1)]
     for name, scene_fn, W, flags, tiles, rows in work:
