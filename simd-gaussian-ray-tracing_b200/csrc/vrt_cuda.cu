@@ -37,6 +37,8 @@ constexpr int BIN_CX = 16;         // cells per coarse bin, x  (128 px)
 constexpr int BIN_CY = 32;         // cells per coarse bin, y  (128 px)
 constexpr int ROOT_SEG = 4096;     // Gaussians per root segment in the first cull level
 constexpr int K2_WARPS = 8;        // warps per render CTA
+// CTA shape per variant: Q = 8 with a 3-CTA/SM target uses 4-warp CTAs (register cap 168, 12 warps/SM)
+__host__ __device__ constexpr int k2_cta_warps(int q, int minb) { return (q == 8 && minb == 3) ? 4 : K2_WARPS; }
 constexpr int STAGE = 32;          // records staged per warp per step (one per lane)
 constexpr int WIN_CAP = 160;       // longest list the depth-window kernel caches per warp ((WIN_CAP+1) * 128 B of prefix sums)
 
@@ -145,7 +147,8 @@ __device__ __forceinline__ float erf_variant(float t)
 // Packed (2 x fp32) forms: Blackwell issues FFMA2 / FMUL2 / FADD2 on 64-bit register pairs, halving the
 // issue slots of the FMA-pipe part of the inner term (the loop is issue-bound in scalar form).
 template <int ERF>
-__device__ __forceinline__ float2 erf_variant2(float2 t)
+/// w(t) = 1 - |erf(t)|, the even part both variants compute first: 1/D(|t|)^4 (A&S) or 2^(-|t| P(|t|)) (exact).
+__device__ __forceinline__ float2 erfc_mag2(float2 t)
 {
     if (ERF == 0)
     {
@@ -156,9 +159,7 @@ __device__ __forceinline__ float2 erf_variant2(float2 t)
         d = __ffma2_rn(d, x, make_float2(1.f, 1.f));
         d = __fmul2_rn(d, d);
         d = __fmul2_rn(d, d);
-        const float2 rc = make_float2(rcp_approx(d.x), rcp_approx(d.y));
-        const float2 v = __ffma2_rn(rc, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
-        return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
+        return make_float2(rcp_approx(d.x), rcp_approx(d.y));
     }
     else
     {
@@ -170,10 +171,16 @@ __device__ __forceinline__ float2 erf_variant2(float2 t)
         p = __ffma2_rn(p, x, make_float2(EX_C1, EX_C1));
         p = __ffma2_rn(p, x, make_float2(EX_C0, EX_C0));
         const float2 q = __fmul2_rn(p, make_float2(-x.x, -x.y));
-        const float2 ex = make_float2(ex2_approx(q.x), ex2_approx(q.y));
-        const float2 v = __ffma2_rn(ex, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
-        return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
+        return make_float2(ex2_approx(q.x), ex2_approx(q.y));
     }
+}
+
+template <int ERF>
+__device__ __forceinline__ float2 erf_variant2(float2 t)
+{
+    const float2 w = erfc_mag2<ERF>(t);
+    const float2 v = __ffma2_rn(w, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+    return make_float2(copysign_bits(v.x, t.x), copysign_bits(v.y, t.y));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -789,10 +796,11 @@ __device__ __forceinline__ PixelRay pixel_ray(int px, int py)
 }
 
 template <int ERF, int Q, bool PACK, int MINB, bool CONTIG, bool WIN>
-__global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArgs args)
+__global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(const RenderArgs args)
 {
-    __shared__ __align__(128) Rec s_rec[K2_WARPS][2][STAGE];
-    __shared__ __align__(8) unsigned long long s_bar[K2_WARPS][2];
+    constexpr int CTA_WARPS = k2_cta_warps(Q, MINB);
+    __shared__ __align__(128) Rec s_rec[CTA_WARPS][2][STAGE];
+    __shared__ __align__(8) unsigned long long s_bar[CTA_WARPS][2];
     const FrameGeom &G = c_geom;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & (CELL_W - 1), ly = lane >> 3;
@@ -918,7 +926,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                 // emission weight sigma c_bar = Kl e / (sqrt(pi/2) log2e)
                 wgt[e] = real ? b.z * ee * (1.f / (SQRT_PI_2 * LOG2E)) : 0.f;
                 any_emit |= real && (ee > args.skip_thresh);
-                if (WIN && real)
+                if (real)
                 {
                     smin = fminf(smin, (mu - s0) - 4.f * b.w);
                     smax = fmaxf(smax, mu - s0);
@@ -947,14 +955,37 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
                     const float A = b.z * e;
                     const float r = b.x;
                     const float nm = -(mu - s0) * r;
+                    // t at the shallowest / deepest sample of the block for this lane (t is monotone in the sample depth)
+                    const float tlo = fmaf(smin, r, nm), thi = fmaf(smax, r, nm);
                     if (WIN)
                     {
-                        // t at the shallowest / deepest sample of the block for this lane
-                        const bool front = fmaf(smin, r, nm) >= tsat, back = fmaf(smax, r, nm) <= -tsat;
-                        if (__all_sync(0xffffffffu, front)) { base = fmaf(A, esat, base); sat += n_real; continue; }
-                        if (__all_sync(0xffffffffu, back)) { base = fmaf(-A, esat, base); sat += n_real; continue; }
+                        if (__all_sync(0xffffffffu, tlo >= tsat)) { base = fmaf(A, esat, base); sat += n_real; continue; }
+                        if (__all_sync(0xffffffffu, thi <= -tsat)) { base = fmaf(-A, esat, base); sat += n_real; continue; }
                     }
                     exec += n_real;
+                    // Sign-uniform occluder: every sample of the block lies behind it (all t >= 0) or in front of it (all t <= 0)
+                    // for every lane -- the common case once the list is depth-sorted.  erf(t) = +-(1 - w(t)) with the sign known
+                    // per (occluder, block): the +-A goes to `base` once, each term only accumulates -+A w(t), which drops the
+                    // per-term sign transfer (LOP3) and the 1 - w from the loop body (8 packed FMA-pipe ops + 1 MUFU per term).
+                    const bool pos = __all_sync(0xffffffffu, tlo >= 0.f);
+                    const bool neg = !pos && __all_sync(0xffffffffu, thi <= 0.f);
+                    if (PACK && (pos || neg))
+                    {
+                        base += pos ? A : -A;
+                        const float sA = pos ? -A : A;
+                        const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(sA, sA);
+#pragma unroll
+                        for (int e2 = 0; e2 < Q / 2; ++e2)
+#pragma unroll
+                            for (int k = 0; k < 5; ++k)
+                            {
+                                const float2 t = __ffma2_rn(make_float2(s[2 * e2][k], s[2 * e2 + 1][k]), rr, mm);
+                                const float2 ac = __ffma2_rn(AA, erfc_mag2<ERF>(t), make_float2(acc[2 * e2][k], acc[2 * e2 + 1][k]));
+                                acc[2 * e2][k] = ac.x;
+                                acc[2 * e2 + 1][k] = ac.y;
+                            }
+                        continue;
+                    }
                     if (PACK)
                     {
                         const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(A, A);
@@ -989,7 +1020,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, MINB) k2_render(const RenderArg
 #pragma unroll
             for (int e = 0; e < Q; ++e)
             {
-                const float Cb = WIN ? C - base : C;
+                const float Cb = C - base;
                 float inner = 3.3546262790251185e-4f * ex2_approx(Cb - acc[e][0]);
                 inner = fmaf(1.1108996538242306e-2f, ex2_approx(Cb - acc[e][1]), inner);
                 inner = fmaf(1.3533528323661270e-1f, ex2_approx(Cb - acc[e][2]), inner);
@@ -1241,7 +1272,7 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float 
 
 // Inner-term ceiling probe: the exact instruction mix of K2's body (per pair of terms 7 FFMA2 + 2 FMUL2 + 2 MUFU.RCP +
 // 2 LOP3) with NP independent pairs per thread and no loads, setup or control flow around it.
-template <int NP>
+template <int NP, bool SIGN_FREE>
 __global__ void __launch_bounds__(256) k_term_peak(float *out, int iters, float r0, float nm0, float a0)
 {
     float2 s[NP], acc[NP];
@@ -1256,7 +1287,8 @@ __global__ void __launch_bounds__(256) k_term_peak(float *out, int iters, float 
     {
         const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(A, A);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) acc[i] = __ffma2_rn(AA, erf_variant2<0>(__ffma2_rn(s[i], rr, mm)), acc[i]);
+        for (int i = 0; i < NP; ++i)
+            acc[i] = SIGN_FREE ? __ffma2_rn(AA, erfc_mag2<0>(__ffma2_rn(s[i], rr, mm)), acc[i]) : __ffma2_rn(AA, erf_variant2<0>(__ffma2_rn(s[i], rr, mm)), acc[i]);
         r += 1e-4f; nm -= 1e-4f; A += 1e-6f;
     }
     float t = 0.f;
@@ -1523,11 +1555,12 @@ template <int ERF, int Q, bool PACK, int MINB, bool CONTIG, bool WIN = false>
 void launch_k2c(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, CONTIG, WIN>, K2_WARPS * 32, 0);
+    constexpr int CTA_WARPS = k2_cta_warps(Q, MINB);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_render<ERF, Q, PACK, MINB, CONTIG, WIN>, CTA_WARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
-    const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
+    const uint32_t want = (a.n_queue + CTA_WARPS - 1) / CTA_WARPS;
     const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-    k2_render<ERF, Q, PACK, MINB, CONTIG, WIN><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+    k2_render<ERF, Q, PACK, MINB, CONTIG, WIN><<<grid, CTA_WARPS * 32, 0, ctx->stream>>>(a);
 }
 
 template <int ERF, int Q, bool PACK, int MINB = (Q <= 4 ? 2 : 1)>
@@ -1573,6 +1606,13 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     }
     // Variants that were measured and dropped (tools/tune_k2.py): Q = 2, 6, 10; 3-4 CTAs/SM by register cap;
     // two occluders per step; sign taken before the reciprocal.  Kept: Q = 8 and 4, packed, and scalar math for comparison.
+    // Q = 8 in 4-warp CTAs, three per SM (168 registers, 12 warps/SM): fastest on the depth-sorted bounded lists, where most
+    // occluders take the cheap sign-uniform body and more warps are needed to cover the per-occluder setup
+    if (ctx->tune_pack == 2 || (ctx->tune_q == 0 && ctx->tune_pack == 1 && q == 8 && ctx->lists_sorted))
+    {
+        launch_k2<ERF, 8, true, 3>(ctx, a);
+        return 0;
+    }
     switch (q)
     {
     case 4: p ? launch_k2<ERF, 4, true>(ctx, a) : launch_k2<ERF, 4, false>(ctx, a); break;
@@ -1672,7 +1712,7 @@ int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int q, int pack)
     if (!ctx) return VRT_CUDA_E_INVALID;
     if (q != 0 && q != 4 && q != 8) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 0 (auto), 4 or 8");
     ctx->tune_q = q;
-    ctx->tune_pack = pack ? 1 : 0;
+    ctx->tune_pack = pack;
     return 0;
 }
 
@@ -1712,10 +1752,12 @@ int vrt_cuda_term_peak(vrt_cuda_ctx *ctx, int pairs, int ctas_per_sm, double *te
         CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         switch (pairs)
         {
-        case 5: k_term_peak<5><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
-        case 10: k_term_peak<10><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
-        case 20: k_term_peak<20><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
-        default: return fail(ctx, VRT_CUDA_E_INVALID, "pairs must be 5, 10 or 20");
+        case 5: k_term_peak<5, false><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        case 10: k_term_peak<10, false><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        case 20: k_term_peak<20, false><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        case -10: k_term_peak<10, true><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break; // sign-uniform body
+        case -20: k_term_peak<20, true><<<blocks, threads, 0, ctx->stream>>>((float *)ctx->counter.p, iters, 1.1f, -0.3f, 0.5f); break;
+        default: return fail(ctx, VRT_CUDA_E_INVALID, "pairs must be 5, 10, 20 (signed body) or -10, -20 (sign-uniform body)");
         }
         CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1723,7 +1765,7 @@ int vrt_cuda_term_peak(vrt_cuda_ctx *ctx, int pairs, int ctas_per_sm, double *te
         CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
         if (rep > 0 && ms < best) best = ms;
     }
-    *terms_per_s_out = (double)blocks * threads * 2.0 * pairs * iters / (best * 1e-3);
+    *terms_per_s_out = (double)blocks * threads * 2.0 * std::abs(pairs) * iters / (best * 1e-3);
     return 0;
 }
 
@@ -1876,7 +1918,9 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
         }
     }
     ctx->lists_sorted = false;
-    if (G.list_kind == 0 && (frame->flags & VRT_CUDA_DEPTH_WINDOW) && ctx->n_entries)
+    // bounded per-cell lists are always depth-sorted: the order is deterministic (ties by index) and makes most occluders
+    // sign-uniform for an emitter block (K2), and saturated in depth-window mode
+    if (G.list_kind == 0 && ctx->n_entries)
     {
         k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
         ctx->launches++;

@@ -28,7 +28,7 @@ def main():
     ]
     variants = [(8, 1), (4, 1), (8, 0), (4, 0)]
     if quick:
-        variants = [(8, 1), (4, 1)]
+        variants = [(8, 1), (4, 1), (8, 2)]
     for name, scene_fn, W, flags, tiles, rows in work:
         if only and name != only:
             continue
