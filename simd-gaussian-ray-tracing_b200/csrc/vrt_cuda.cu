@@ -33,8 +33,6 @@ namespace
 {
 constexpr int CELL_W = 8;          // pixels per cell (= one warp), x
 constexpr int CELL_H = 4;          // y
-constexpr int BIN_CX = 16;         // cells per coarse bin, x  (128 px)
-constexpr int BIN_CY = 32;         // cells per coarse bin, y  (128 px)
 constexpr int ROOT_SEG = 4096;     // Gaussians per root segment in the first cull level
 constexpr int K2_WARPS = 8;        // warps per render CTA
 // CTA shape per variant: Q = 8 with a 3-CTA/SM target uses 4-warp CTAs (register cap 168, 12 warps/SM)
@@ -57,8 +55,8 @@ struct FrameGeom
     int tiles_x, tiles_y, tile_w, tile_h;
     int cptx, cpty;   // cells per tile
     int ncx, ncy;     // global cell grid
-    int nbx, nby;     // coarse bins
     int row_begin, row_end;
+    int uniform;      // every tile is a whole number of cells and cells tile the image exactly: cell (cx, cy) starts at (8 cx, 4 cy)
     // list semantics
     int use_ref;      // apply the reference predicate
     int use_bound;    // apply the per-cell k-sigma bound
@@ -186,7 +184,7 @@ __device__ __forceinline__ float2 erf_variant2(float2 t)
 // ------------------------------------------------------------------------------------------------
 // K0: per-Gaussian frame constants
 // ------------------------------------------------------------------------------------------------
-// cull record: (mu'.x, mu'.y, 3.3 sigma', valid) of the reference's tiling projection (rt.cpp:35-45)
+// cull record, 32 B: (oc.xyz, sigma) and (mu'.x, mu'.y, 3.3 sigma', valid) of the reference's tiling projection (rt.cpp:35-45)
 __global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__restrict__ rec, float4 *__restrict__ cullrec)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,7 +209,9 @@ __global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__res
         const float inv = 1.f / pz;
         const float sg = sigma * inv;
         const bool valid = !(pz < 1.f) && !(sg < 1e-5f);
-        cullrec[i] = make_float4(px * inv, py * inv, REF_CULL_SIGMAS * sg, valid ? 1.f : 0.f);
+        // one 32-byte sector per Gaussian holds everything K1 tests: (oc.xyz, sigma) and the reference projection
+        cullrec[2 * i] = make_float4(r.a.x, r.a.y, r.a.z, sigma);
+        cullrec[2 * i + 1] = make_float4(px * inv, py * inv, REF_CULL_SIGMAS * sg, valid ? 1.f : 0.f);
     }
 }
 
@@ -222,9 +222,7 @@ struct CullRect
 {
     // outward unit normals of the four side planes of the rect's ray frustum (apex = origin)
     float nl[3], nr[3], nb[3], nt[3];
-    // unit directions of the four corner rays (u0,v0) (u1,v0) (u0,v1) (u1,v1)
-    float e00[3], e10[3], e01[3], e11[3];
-    float c00, c10, c01, c11; // cosines between the adjacent planes' normals at those corners
+    float u0, u1, v0, v1;   // plane coordinates of the extreme pixel samples (the corner rays)
     int tx0, tx1, ty0, ty1; // reference tile range covered
     bool exact_tile;        // single tile: evaluate the predicate exactly
 };
@@ -244,42 +242,58 @@ __device__ __forceinline__ void orient_normalize(float *n, const float *towards,
 }
 
 // pixel rect [x0,x1) x [y0,y1) -> frustum planes through the extreme sample positions
-__device__ void make_rect(int x0, int x1, int y0, int y1, CullRect &rc)
+__device__ __forceinline__ void make_rect(int x0, int x1, int y0, int y1, CullRect &rc)
 {
     const FrameGeom &G = c_geom;
-    const float u0 = -1.f + (float)x0 / G.half_w, u1 = -1.f + (float)(x1 - 1) / G.half_w;
-    const float v0 = -1.f + (float)y0 / G.half_h, v1 = -1.f + (float)(y1 - 1) / G.half_h;
+    rc.u0 = -1.f + (float)x0 / G.half_w; rc.u1 = -1.f + (float)(x1 - 1) / G.half_w;
+    rc.v0 = -1.f + (float)y0 / G.half_h; rc.v1 = -1.f + (float)(y1 - 1) / G.half_h;
     float Wv[3], a[3];
     for (int i = 0; i < 3; ++i) Wv[i] = G.inv3[i] - G.origin[i];
     // left / right planes contain U = inv1 and the ray (u * inv0 + Wv)
-    for (int i = 0; i < 3; ++i) a[i] = u0 * G.inv0[i] + Wv[i];
+    for (int i = 0; i < 3; ++i) a[i] = rc.u0 * G.inv0[i] + Wv[i];
     cross3(G.inv1, a, rc.nl); orient_normalize(rc.nl, G.inv0, -1.f);
-    for (int i = 0; i < 3; ++i) a[i] = u1 * G.inv0[i] + Wv[i];
+    for (int i = 0; i < 3; ++i) a[i] = rc.u1 * G.inv0[i] + Wv[i];
     cross3(G.inv1, a, rc.nr); orient_normalize(rc.nr, G.inv0, +1.f);
     // bottom / top planes contain R = inv0 and the ray (v * inv1 + Wv)
-    for (int i = 0; i < 3; ++i) a[i] = v0 * G.inv1[i] + Wv[i];
+    for (int i = 0; i < 3; ++i) a[i] = rc.v0 * G.inv1[i] + Wv[i];
     cross3(G.inv0, a, rc.nb); orient_normalize(rc.nb, G.inv1, -1.f);
-    for (int i = 0; i < 3; ++i) a[i] = v1 * G.inv1[i] + Wv[i];
+    for (int i = 0; i < 3; ++i) a[i] = rc.v1 * G.inv1[i] + Wv[i];
     cross3(G.inv0, a, rc.nt); orient_normalize(rc.nt, G.inv1, +1.f);
+    rc.tx0 = rc.tx1 = rc.ty0 = rc.ty1 = 0;
+    if (G.use_ref)
     {
-        const float us[2] = {u0, u1}, vs[2] = {v0, v1};
-        float *es[4] = {rc.e00, rc.e10, rc.e01, rc.e11};
-        for (int c = 0; c < 4; ++c)
-        {
-            float *e = es[c];
-            for (int i = 0; i < 3; ++i) e[i] = us[c & 1] * G.inv0[i] + vs[c >> 1] * G.inv1[i] + Wv[i];
-            const float inv = rsqrtf(fmaxf(dot3(e, e), 1e-30f));
-            e[0] *= inv; e[1] *= inv; e[2] *= inv;
-        }
+        rc.tx0 = x0 / G.tile_w; rc.tx1 = (x1 - 1) / G.tile_w;
+        rc.ty0 = y0 / G.tile_h; rc.ty1 = (y1 - 1) / G.tile_h;
     }
-    rc.c00 = dot3(rc.nl, rc.nb); rc.c10 = dot3(rc.nr, rc.nb); rc.c01 = dot3(rc.nl, rc.nt); rc.c11 = dot3(rc.nr, rc.nt);
-    rc.tx0 = x0 / G.tile_w; rc.tx1 = (x1 - 1) / G.tile_w;
-    rc.ty0 = y0 / G.tile_h; rc.ty1 = (y1 - 1) / G.tile_h;
     rc.exact_tile = (rc.tx0 == rc.tx1) && (rc.ty0 == rc.ty1);
 }
 
 // reference predicate for one axis (src/vrt/rt.cpp:57-59): |c - mu'| <= |c| + t/2 + 3.3 sigma'
 __device__ __forceinline__ bool ref_axis(float c, float mu, float half_t, float s33) { return fabsf(c - mu) <= fabsf(c) + half_t + s33; }
+
+// Distance test against one orientation of the frustum (sgn = +1: the frustum itself, -1: its mirror image through the
+// apex).  Inside the k-sigma slab of all four planes; a centre outside TWO adjacent planes (distances su, sv > 0, cosine c
+// between their normals) is nearest to the corner ray only if it projects beyond the edge on BOTH faces (su - sv c > 0 and
+// sv - su c > 0) -- then its distance to that ray's line decides (rounded corners instead of a box: ~14 % shorter lists);
+// otherwise a face is nearest and its plane distance (already <= lim) is the true distance.
+__device__ __forceinline__ bool near_frustum(const CullRect &rc, const float *p, float dl, float dr, float db, float dt, float sgn, float lim)
+{
+    const FrameGeom &G = c_geom;
+    const float sl = sgn * dl, sr = sgn * dr, sb = sgn * db, st = sgn * dt;
+    const float su = fmaxf(sl, sr), sv = fmaxf(sb, st);
+    if (!(su <= lim && sv <= lim)) return false;
+    if (!(su > 0.f && sv > 0.f)) return true;
+    const bool right = sr > sl, top = st > sb;
+    float c = 0.f;
+    for (int i = 0; i < 3; ++i) c += (right ? rc.nr[i] : rc.nl[i]) * (top ? rc.nt[i] : rc.nb[i]);
+    if (!(su - sv * c > 0.f && sv - su * c > 0.f)) return true;
+    const float uu = right ? rc.u1 : rc.u0, vv = top ? rc.v1 : rc.v0;
+    float e[3];
+    for (int i = 0; i < 3; ++i) e[i] = uu * G.inv0[i] + vv * G.inv1[i] + (G.inv3[i] - G.origin[i]);
+    const float t = __fdividef(dot3(p, e), dot3(e, e));
+    const float px = p[0] - t * e[0], py = p[1] - t * e[1], pz = p[2] - t * e[2];
+    return px * px + py * py + pz * pz <= lim * lim;
+}
 
 __device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, const float sigma, const float4 cr)
 {
@@ -308,35 +322,9 @@ __device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, co
         // distance budget: k sigma, plus the w offset can only increase the true distance (ignored => conservative)
         const float lim = G.bound_k * sigma + 1e-6f * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z));
         const float dl = dot3(p, rc.nl), dr = dot3(p, rc.nr), db = dot3(p, rc.nb), dt = dot3(p, rc.nt);
-        // Inside the k-sigma slab of all four planes; a centre that is outside TWO adjacent planes is nearest to the corner
-        // ray, so its distance to that ray's line decides (rounded corners instead of a box: ~14 % shorter lists).
-        auto near_frustum = [&](float sl, float sr, float sb, float st) -> bool {
-            if (!(sl <= lim && sr <= lim && sb <= lim && st <= lim)) return false;
-            // outside two adjacent planes (distances su, sv > 0, cosine c between their normals): the corner ray is the
-            // nearest feature only if the centre projects beyond the edge on BOTH faces (su - sv c > 0 and sv - su c > 0);
-            // otherwise a face is nearest and its plane distance (already <= lim) is the true distance
-            const float *e = nullptr;
-            float su = 0.f, sv = 0.f, c = 0.f;
-            if (sb > 0.f)
-            {
-                if (sl > 0.f) { e = rc.e00; su = sl; sv = sb; c = rc.c00; }
-                else if (sr > 0.f) { e = rc.e10; su = sr; sv = sb; c = rc.c10; }
-            }
-            else if (st > 0.f)
-            {
-                if (sl > 0.f) { e = rc.e01; su = sl; sv = st; c = rc.c01; }
-                else if (sr > 0.f) { e = rc.e11; su = sr; sv = st; c = rc.c11; }
-            }
-            if (e == nullptr || !(su - sv * c > 0.f && sv - su * c > 0.f)) return true;
-            const float q = dot3(p, e);
-            const float px = p[0] - q * e[0], py = p[1] - q * e[1], pz = p[2] - q * e[2];
-            return px * px + py * py + pz * pz <= lim * lim;
-        };
-        const bool front = near_frustum(dl, dr, db, dt);
         // the reference integrates along the whole line (samples with s < 0 are not guarded, rt.h:155-160),
         // so the mirrored frustum counts too
-        const bool back = near_frustum(-dl, -dr, -db, -dt);
-        if (!(front || back)) return false;
+        if (!(near_frustum(rc, p, dl, dr, db, dt, 1.f, lim) || near_frustum(rc, p, dl, dr, db, dt, -1.f, lim))) return false;
     }
     return true;
 }
@@ -370,10 +358,20 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
     // pixel rect of the group = union of its cells' rects
     const int cx0 = gxi * L.gx, cx1 = min(G.ncx, cx0 + L.gx) - 1;
     const int cy0 = gyi * L.gy, cy1 = min(G.ncy, cy0 + L.gy) - 1;
-    const int x0 = (cx0 / G.cptx) * G.tile_w + (cx0 % G.cptx) * CELL_W;
-    const int y0 = (cy0 / G.cpty) * G.tile_h + (cy0 % G.cpty) * CELL_H;
-    const int x1 = min((cx1 / G.cptx) * G.tile_w + min(G.tile_w, (cx1 % G.cptx + 1) * CELL_W), G.W);
-    const int y1 = min((cy1 / G.cpty) * G.tile_h + min(G.tile_h, (cy1 % G.cpty + 1) * CELL_H), G.H);
+    int x0, y0, x1, y1;
+    if (G.uniform)
+    {
+        x0 = cx0 * CELL_W; y0 = cy0 * CELL_H;
+        x1 = (cx1 + 1) * CELL_W; y1 = (cy1 + 1) * CELL_H;
+    }
+    else
+    {
+        // ragged tiles (tile size not a multiple of the cell): cells restart at every tile edge
+        x0 = (cx0 / G.cptx) * G.tile_w + (cx0 % G.cptx) * CELL_W;
+        y0 = (cy0 / G.cpty) * G.tile_h + (cy0 % G.cpty) * CELL_H;
+        x1 = min((cx1 / G.cptx) * G.tile_w + min(G.tile_w, (cx1 % G.cptx + 1) * CELL_W), G.W);
+        y1 = min((cy1 / G.cpty) * G.tile_h + min(G.tile_h, (cy1 % G.cpty + 1) * CELL_H), G.H);
+    }
     uint32_t begin, end;
     if (L.is_root)
     {
@@ -402,10 +400,9 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
             if (e < end)
             {
                 gi = L.is_root ? e : parent_idx[e];
-                const float4 a = rec[gi].a;
-                const float sigma = rec[gi].b.w;
-                const float4 cr = G.use_ref ? cullrec[gi] : make_float4(0.f, 0.f, 0.f, 1.f);
-                pass = cull_test(rc, a, sigma, cr);
+                const float4 a = cullrec[2 * gi]; // (oc.xyz, sigma)
+                const float4 cr = G.use_ref ? cullrec[2 * gi + 1] : make_float4(0.f, 0.f, 0.f, 1.f);
+                pass = cull_test(rc, a, a.w, cr);
             }
             const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
             if (WRITE)
@@ -450,7 +447,7 @@ __global__ void __launch_bounds__(256) k1_cull_tiles(const Rec *__restrict__ rec
         bool pass = false;
         if (i < n_root)
         {
-            const float4 cr = cullrec[i];
+            const float4 cr = cullrec[2 * i + 1];
             pass = cr.w != 0.f && ref_axis(cx, cr.x, hx, cr.z) && ref_axis(cy, cr.y, hy, cr.z);
         }
         const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
@@ -476,7 +473,7 @@ __global__ void __launch_bounds__(256) k1_cull_tiles(const Rec *__restrict__ rec
 // lists longer than SORT_CAP stay in index order (the window test is valid for any order, it just saturates less often).
 constexpr int SORT_CAP = 512;
 __device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int &w, int &h);
-__global__ void __launch_bounds__(128) k1_sort_cells(const Rec *__restrict__ rec, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ list_idx,
+__global__ void __launch_bounds__(128) k1_sort_cells(const float4 *__restrict__ cullrec, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ list_idx,
                                                      uint32_t n_cells)
 {
     __shared__ float s_key[4][SORT_CAP];
@@ -503,7 +500,7 @@ __global__ void __launch_bounds__(128) k1_sort_cells(const Rec *__restrict__ rec
         if (i < n)
         {
             const uint32_t gi = list_idx[off + i];
-            const float4 a = rec[gi].a;
+            const float4 a = cullrec[2 * gi];
             key[i] = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
             val[i] = gi;
         }
@@ -588,6 +585,12 @@ __device__ __forceinline__ uint32_t cell_list_id(int cx, int cy)
 __device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int &w, int &h)
 {
     const FrameGeom &G = c_geom;
+    if (G.uniform)
+    {
+        x0 = cx * CELL_W; y0 = cy * CELL_H;
+        w = CELL_W; h = CELL_H;
+        return;
+    }
     const int lx = (cx % G.cptx) * CELL_W, ly = (cy % G.cpty) * CELL_H;
     x0 = (cx / G.cptx) * G.tile_w + lx;
     y0 = (cy / G.cpty) * G.tile_h + ly;
@@ -1452,8 +1455,7 @@ int make_geom(vrt_cuda_ctx *ctx, const vrt_cuda_frame *f, int list_kind_override
     G.cpty = (G.tile_h + CELL_H - 1) / CELL_H;
     G.ncx = G.tiles_x * G.cptx;
     G.ncy = G.tiles_y * G.cpty;
-    G.nbx = (G.ncx + BIN_CX - 1) / BIN_CX;
-    G.nby = (G.ncy + BIN_CY - 1) / BIN_CY;
+    G.uniform = (G.tile_w % CELL_W == 0 && G.tile_h % CELL_H == 0) ? 1 : 0;
     G.row_begin = (int)f->row_begin;
     G.row_end = (int)f->row_end;
     if (f->row_begin == 0 && f->row_end == 0) G.row_end = G.H;
@@ -1821,7 +1823,7 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 
     if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(N, 1))) return rc;
-    if (int rc = reserve(ctx, ctx->cullrec, sizeof(float4) * std::max<uint64_t>(N, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->cullrec, 2 * sizeof(float4) * std::max<uint64_t>(N, 1))) return rc;
     if (N)
     {
         k0_prepare<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->aos.p, N, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p);
@@ -1922,7 +1924,7 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     // sign-uniform for an emitter block (K2), and saturated in depth-window mode
     if (G.list_kind == 0 && ctx->n_entries)
     {
-        k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
+        k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
         ctx->launches++;
         ctx->lists_sorted = true;
     }
