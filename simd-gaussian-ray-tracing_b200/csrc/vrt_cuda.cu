@@ -562,6 +562,64 @@ __global__ void __launch_bounds__(1024) k1_scan(const uint32_t *__restrict__ cou
     if (threadIdx.x == 1023) offsets[n] = s_part[1023];
 }
 
+// Large arrays are scanned in three launches: per-tile sums (SCAN_TILE elements per CTA), k1_scan over the tile sums,
+// then every CTA rescans its tile starting from its tile offset.
+constexpr int SCAN_TILE = 4096; // 256 threads x 16 consecutive elements
+__device__ __forceinline__ uint32_t block_exclusive_256(uint32_t v, uint32_t *s_warp, uint32_t &block_total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int q = 0; q < 8; ++q)
+    {
+        const uint32_t c = s_warp[q];
+        if (q < w) before += c;
+        total += c;
+    }
+    block_total = total;
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k1_scan_tiles(const uint32_t *__restrict__ counts, uint32_t *__restrict__ tile_sums, uint32_t n)
+{
+    __shared__ uint32_t s_warp[8];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 16;
+    uint32_t sum = 0;
+    for (int i = 0; i < 16; ++i)
+        if (base + i < n) sum += counts[base + i];
+    uint32_t total;
+    block_exclusive_256(sum, s_warp, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k1_scan_apply(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tile_offsets,
+                                                     uint32_t *__restrict__ offsets, uint32_t n, uint32_t n_tiles)
+{
+    __shared__ uint32_t s_warp[8];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 16;
+    uint32_t v[16], sum = 0;
+    for (int i = 0; i < 16; ++i)
+    {
+        v[i] = base + i < n ? counts[base + i] : 0u;
+        sum += v[i];
+    }
+    uint32_t total;
+    uint32_t run = tile_offsets[blockIdx.x] + block_exclusive_256(sum, s_warp, total);
+    for (int i = 0; i < 16; ++i)
+    {
+        if (base + i < n) offsets[base + i] = run;
+        run += v[i];
+    }
+    if (blockIdx.x == n_tiles - 1 && threadIdx.x == 255) offsets[n] = tile_offsets[n_tiles]; // grand total
+}
+
 // statistics + cost histogram of the render cells.  list id of a cell: per-cell lists -> cell, per-tile ->
 // its tile, single -> 0.  key = min(n, 65535); the queue is filled in descending key order.
 struct TileStats
@@ -1198,8 +1256,9 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
                 break;
             }
             bk = max(bk, f);
-            const float base = esat * (sm.prefix[f][lane] - (total - sm.prefix[bk][lane]));
+            float base = esat * (sm.prefix[f][lane] - (total - sm.prefix[bk][lane]));
             sat += (unsigned long long)(f + (n - bk)) * n_real;
+            const float smin0 = smin - s0, smax0 = smax - s0;
 
             for (uint32_t j = f; j < bk; ++j)
             {
@@ -1209,6 +1268,26 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
                 if (!__any_sync(0xffffffffu, e > args.skip_thresh)) continue;
                 const float A = b.z * e, r = b.x, nm = -(mu - s0) * r;
                 exec += n_real;
+                // sign-uniform occluder (see k2_render): +-A once, -+A w(t) per term
+                const bool pos = __all_sync(0xffffffffu, fmaf(smin0, r, nm) >= 0.f);
+                const bool neg = !pos && __all_sync(0xffffffffu, fmaf(smax0, r, nm) <= 0.f);
+                if (pos || neg)
+                {
+                    base += pos ? A : -A;
+                    const float sA = pos ? -A : A;
+                    const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(sA, sA);
+#pragma unroll
+                    for (int e2 = 0; e2 < Q / 2; ++e2)
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                        {
+                            const float2 t = __ffma2_rn(make_float2(s[2 * e2][k], s[2 * e2 + 1][k]), rr, mm);
+                            const float2 ac = __ffma2_rn(AA, erfc_mag2<ERF>(t), make_float2(acc[2 * e2][k], acc[2 * e2 + 1][k]));
+                            acc[2 * e2][k] = ac.x;
+                            acc[2 * e2 + 1][k] = ac.y;
+                        }
+                    continue;
+                }
                 const float2 rr = make_float2(r, r), mm = make_float2(nm, nm), AA = make_float2(A, A);
 #pragma unroll
                 for (int e2 = 0; e2 < Q / 2; ++e2)
@@ -1353,7 +1432,7 @@ struct vrt_cuda_ctx
     DevBuf cullrec;    // reference tiling projection
     DevBuf lvl_counts[4], lvl_offsets[4], lvl_idx[4], lvl_group_off; // coarse culling levels
     DevBuf ccounts, coffsets, cidx;       // level 1 (cells / tiles)
-    DevBuf hist, queue, stats, counter, rowcost;
+    DevBuf hist, queue, stats, counter, rowcost, scan_tmp;
     DevBuf out_image, out_rad;
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
     DevBuf tile_off;
@@ -1501,6 +1580,25 @@ int upload_geom(vrt_cuda_ctx *ctx, const FrameGeom &G, const std::vector<float> 
     CU(cudaMemcpyToSymbolAsync(c_geom, &G, sizeof(G), 0, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyToSymbolAsync(c_tile_cx, cxs.data(), sizeof(float) * 1024, 0, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyToSymbolAsync(c_tile_cy, cys.data(), sizeof(float) * 1024, 0, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// exclusive scan of `n` counts into n + 1 offsets on the context's stream
+int scan_u32(vrt_cuda_ctx *ctx, const uint32_t *counts, uint32_t *offsets, uint32_t n)
+{
+    if (n <= 4 * SCAN_TILE)
+    {
+        k1_scan<<<1, 1024, 0, ctx->stream>>>(counts, offsets, n);
+        ctx->launches++;
+        return 0;
+    }
+    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (int rc = reserve(ctx, ctx->scan_tmp, sizeof(uint32_t) * (2 * (size_t)n_tiles + 2))) return rc;
+    uint32_t *sums = (uint32_t *)ctx->scan_tmp.p, *offs = sums + n_tiles;
+    k1_scan_tiles<<<n_tiles, 256, 0, ctx->stream>>>(counts, sums, n);
+    k1_scan<<<1, 1024, 0, ctx->stream>>>(sums, offs, n_tiles);
+    k1_scan_apply<<<n_tiles, 256, 0, ctx->stream>>>(counts, offs, offsets, n, n_tiles);
+    ctx->launches += 3;
     return 0;
 }
 
@@ -1667,7 +1765,7 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
-                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
+                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 4; ++i)
@@ -1889,14 +1987,14 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
             const unsigned grid = (unsigned)((work * 32 + 255) / 256);
             k1_cull<false><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx,
                                                          (uint32_t *)cnt.p, nullptr, nullptr, (uint32_t)work);
-            k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)cnt.p, (uint32_t *)off.p, (uint32_t)work);
+            if (int rc = scan_u32(ctx, (const uint32_t *)cnt.p, (uint32_t *)off.p, (uint32_t)work)) return rc;
             uint32_t total = 0;
             CU(cudaMemcpyAsync(&total, (const uint32_t *)off.p + work, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             if (int rc = reserve(ctx, idx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
             k1_cull<true><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx, nullptr,
                                                         (const uint32_t *)off.p, (uint32_t *)idx.p, (uint32_t)work);
-            ctx->launches += 3;
+            ctx->launches += 2;
             parent_idx = (const uint32_t *)idx.p;
             if (L.n_seg > 1)
             {
