@@ -314,7 +314,9 @@ def run_cuda(args, pkg, cfg, rank, world):
         "peak_source": f"nominal: {sm_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (max SM clock, MEASURED_PEAKS.json); MEASURED_PEAKS has no fp32 figure",
         "measured_ffma_tflops": ffma, "measured_ffma2_tflops": ffma2, "frac_of_measured_ffma": achieved / max(ffma, ffma2),
         "flops_per_term": FLOPS_PER_TERM, "terms_per_launch": k2_terms, "ms_per_launch": float(np.mean([s["ms_render"] for s in stats])),
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k2_render launch of this command under `ncu --set full`
+        # (profiles/r01_k2_render_final_ncu_raw.csv: 358.1 MB + 63.8 MB); algorithmic: 48 MB records + 172 MB lists + 67 MB image
+        "traffic": 421867776 if args.config == 5 and world == 1 else None, "traffic_unit": "bytes per launch (ncu, round-1 capture)",
     }
     line = {
         "metric": "pixel-Gaussian evaluations/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

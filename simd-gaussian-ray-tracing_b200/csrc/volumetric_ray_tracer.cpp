@@ -26,26 +26,18 @@
 #include "vrt_host.h"
 #include "vrt_types.hpp"
 
-#define HELP_MSG                                                                                                      \
-    "Usage: volumetric-ray-tracer [options]\n\nOptions:\n"                                                            \
-    "\t--help:                                 Show this help message.\n"                                             \
-    "\t--file <file>, -f <file>:               Load gaussians as verticies from <file> (.obj).\n"                     \
-    "\t--output <file>, -o <file>:             Write image to <file> as in PNG format.\n"                             \
-    "\t--grid <dim=4>, -g <dim=4>:             Render a grid of <dim>x<dim> gaussians. Overrides --file.\n"           \
-    "\t--width <width>, -w <width>:            Set image width (and height if --height is not set).\n"                \
-    "\t--height <height>, -h <height>:         Set image height (and width if --width is not set).\n"                 \
-    "\t--with-threads <count>, -t <count>:     Accepted for compatibility; the GPU grid replaces the thread pool.\n"   \
-    "\t--quiet, -q:                            Quit after rendering (this build is always headless).\n"               \
-    "\t--frames <count>:                       Render <count> frames.\n"                                              \
-    "\t--tiles <count>:                        Split the image into <count> tiles vertically and horizontally.\n"     \
-    "\t--rotation <rot>, -r <rot>:             Total change of the viewing angle over all frames.\n"                  \
-    "\t--initial-rotation <rot>, -i <rot>:     Sets the initial rotation to <rot>.\n"                                 \
-    "\t--camera-offset <offset>, -c <offset>:  Set the position of the camera along the Z-Axis to <offset>.\n"        \
-    "\t--focal-length <focal-length>:          Set the focal length of the camera.\n"                                 \
-    "\t--mode <mode>, -m <mode>:               1-8 as the reference; 9 untiled+bound; 10 tiled reference AND bound (default).\n" \
-    "\t--gpus <n>:                             Render row bands on <n> GPUs.\n"                                       \
-    "\t--bound <k>:                            k-sigma bound of modes 9/10 (default 6).\n"                            \
-    "\t--synthetic <n> [--seed <s>] [--sigma-range <lo>,<hi>]: random frustum-filling scene (log10 sigma range).\n"
+static const char *const HELP_MSG =
+    "volumetric-ray-tracer (CUDA, headless)\n"
+    "  scene     -g [dim]              dim x dim Gaussian grid (default 4; wins over nothing, loses to -f)\n"
+    "            -f <obj>              one Gaussian per OBJ vertex\n"
+    "            --synthetic <n>       n random Gaussians filling the view frustum [--seed <s>] [--sigma-range <lo>,<hi> (log10)]\n"
+    "  image     -w <px> / -h <px>     size (one of them sets both), --tiles <n> reference tiles per axis (16)\n"
+    "            -o <file.png>         write the frame(s); <file>_<k>.png when --frames > 1\n"
+    "  camera    -c <z> (-4), --focal-length <f> (1), -i <deg> start angle, -r <deg> total turn over --frames <n>\n"
+    "  render    -m <mode>             1-8: the reference's modes (erf variant, lists, quantisation, alpha)\n"
+    "                                  9: untiled semantics + k-sigma lists, 10: tiled semantics + k-sigma lists (default)\n"
+    "            --bound <k> (6)       k of modes 9/10;   --gpus <n> row bands on n GPUs\n"
+    "  misc      -q (always headless), -t <n> (ignored: no thread pool), --help\n";
 
 struct cmd_args_t
 {
