@@ -39,6 +39,12 @@ constexpr int K2_WARPS = 8;        // warps per render CTA
 __host__ __device__ constexpr int k2_cta_warps(int q, int minb) { return (q == 8 && minb == 3) ? 4 : K2_WARPS; }
 constexpr int STAGE = 32;          // records staged per warp per step (one per lane)
 constexpr int WIN_CAP = 160;       // longest list the depth-window kernel caches per warp ((WIN_CAP+1) * 128 B of prefix sums)
+// Heavy cells (work ~ n^2) are split by emitter range into independent work items so one warp never owns a whole long list:
+// a cell with more than SPLIT_MIN entries becomes ceil(n / SLICE) items; the partial radiances are summed in slice order.
+constexpr int SPLIT_MIN = 192;
+constexpr int SLICE = 64;          // emitters per item of a split cell (a multiple of every emitter block size Q)
+constexpr int ITEM_CELL_BITS = 22; // work item = cell id | slice << 22  (4M cells, 1024 slices)
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float SQRT_PI_2 = 1.2533141373155003f; // sqrt(pi/2) = 1/0.7978845608 (INV_SQRT_2_PI of src/vrt/rt.h:19)
@@ -629,7 +635,9 @@ struct TileStats
     double terms_listed;          // sum over band pixels of 5 n^2
     unsigned long long terms_exec; // filled by K2
     unsigned long long terms_sat;  // K2, depth-window mode: terms resolved by saturation
-    unsigned long long n_big;      // queued cells whose list is longer than the depth-window cache
+    unsigned long long n_big;      // queued items whose list is longer than the depth-window cache
+    unsigned long long n_items;    // work items queued (cells + extra slices of split cells)
+    unsigned long long n_split;    // items that belong to split cells (= partial-radiance slots)
 };
 
 __device__ __forceinline__ uint32_t cell_list_id(int cx, int cy)
@@ -656,6 +664,14 @@ __device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int 
     h = min(CELL_H, G.tile_h - ly);
 }
 
+// number of work items of a cell with an n-entry list
+__device__ __forceinline__ uint32_t cell_items(uint32_t n, uint32_t cell)
+{
+    if (n <= (uint32_t)SPLIT_MIN || cell >= (1u << ITEM_CELL_BITS)) return 1u;
+    const uint32_t k = (n + SLICE - 1) / SLICE;
+    return k <= (1u << (32 - ITEM_CELL_BITS)) ? k : 1u;
+}
+
 __global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
                         double *__restrict__ row_cost, int cy_begin, int cy_end)
 {
@@ -674,7 +690,10 @@ __global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restr
         if (yb > ya)
         {
             terms = 5.0 * (double)n * (double)n * (double)(w * (yb - ya));
-            atomicAdd(&hist[min(n, 65535u)], 1u);
+            const uint32_t items = cell_items(n, (uint32_t)(cy * G.ncx + cx));
+            atomicAdd(&hist[min(n, 65535u)], items);
+            atomicAdd(&stats->n_items, (unsigned long long)items);
+            if (items > 1) atomicAdd(&stats->n_split, (unsigned long long)items);
             if (row_cost != nullptr) atomicAdd(&row_cost[cy], terms);
         }
     }
@@ -729,7 +748,8 @@ __global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist
     }
 }
 
-__global__ void k1_order(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, int cy_begin, int cy_end)
+__global__ void k1_order(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, uint32_t *__restrict__ cell_slot,
+                         uint32_t *__restrict__ split_cursor, int cy_begin, int cy_end)
 {
     const FrameGeom &G = c_geom;
     const int ncells = (cy_end - cy_begin) * G.ncx;
@@ -741,8 +761,13 @@ __global__ void k1_order(const uint32_t *__restrict__ list_off, uint32_t *__rest
     if (min(y0 + h, G.row_end) <= max(y0, G.row_begin)) return;
     const uint32_t id = cell_list_id(cx, cy);
     const uint32_t n = list_off[id + 1] - list_off[id];
-    const uint32_t pos = atomicAdd(&cursor[min(n, 65535u)], 1u);
-    queue[pos] = (uint32_t)(cy * G.ncx + cx);
+    const uint32_t cell = (uint32_t)(cy * G.ncx + cx);
+    const uint32_t items = cell_items(n, cell);
+    const uint32_t pos = atomicAdd(&cursor[min(n, 65535u)], items);
+    for (uint32_t k = 0; k < items; ++k) queue[pos + k] = cell | (k << ITEM_CELL_BITS);
+    // split cells get `items` consecutive slots of the partial-radiance buffer (the slot order is irrelevant: K3' sums a
+    // cell's slices in slice order)
+    cell_slot[cell] = items > 1 ? atomicAdd(split_cursor, items) : NO_SLOT;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -763,6 +788,8 @@ struct RenderArgs
     float skip_thresh;         // skip an occluder / emitter for the whole warp when exp2 weight <= thresh (-1: never)
     uint32_t quant_nearest, alpha_from_w;
     uint32_t window; // depth-window mode
+    const uint32_t *cell_slot; // per cell: first slot of its slices in `partial`, NO_SLOT for whole cells (may be null)
+    float4 *partial;           // [slot][lane] partial radiance of the items of split cells
 };
 
 // ---- per-warp record staging -------------------------------------------------------------------------------------------
@@ -887,7 +914,8 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
         if (lane == 0) qi = atomicAdd(args.counter, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= args.n_queue) break;
-        const uint32_t cell = args.queue[qi];
+        const uint32_t item = args.queue[qi];
+        const uint32_t cell = item & ((1u << ITEM_CELL_BITS) - 1u), slice = item >> ITEM_CELL_BITS;
         const int cx = cell % G.ncx, cy = cell / G.ncx;
         int x0, y0, cw, ch;
         cell_rect(cx, cy, x0, y0, cw, ch);
@@ -962,7 +990,10 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 
         // ---- pass B: emitters in blocks of Q, all occluders per block ----
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
-        for (uint32_t q0 = 0; q0 < n; q0 += Q)
+        // a split cell's item covers the emitters [q_begin, q_end) only; every item still needs all n occluders
+        const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * SLICE : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + SLICE) : n;
+        for (uint32_t q0 = q_begin; q0 < q_end; q0 += Q)
         {
             // emitter block
             float s[Q][5], acc[Q][5], wgt[Q];
@@ -972,7 +1003,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 #pragma unroll
             for (int e = 0; e < Q; ++e)
             {
-                const bool real = q0 + e < n;
+                const bool real = q0 + e < q_end;
                 const Rec *r = load_rec(real ? q0 + e : q0);
                 const float4 a = r->a, b = r->b;
                 alb[e] = r->c;
@@ -1000,7 +1031,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
                 }
             }
             if (!__any_sync(0xffffffffu, any_emit)) continue; // no lane sees any of these emitters
-            const uint32_t n_real = min((uint32_t)Q, n - q0);
+            const uint32_t n_real = min((uint32_t)Q, q_end - q0);
 
             if (!resident) begin_pass();
             for (uint32_t c = 0; c < n_chunks; ++c)
@@ -1096,12 +1127,41 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
         }
 
         // ---- K3: framebuffer ----
-        if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
+        else if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
         if (WIN && lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
         exec = 0;
         sat = 0;
     }
+}
+
+// K3', split cells: sum the slices' partial radiances in slice order (deterministic) and write the pixel.
+__global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, const uint32_t *__restrict__ list_off, int cy_begin, int cy_end)
+{
+    const FrameGeom &G = c_geom;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t ncells = (uint32_t)((cy_end - cy_begin) * G.ncx);
+    if (w >= ncells) return;
+    const int cx = (int)(w % G.ncx), cy = cy_begin + (int)(w / G.ncx);
+    const uint32_t cell = (uint32_t)(cy * G.ncx + cx);
+    int x0, y0, cw, ch;
+    cell_rect(cx, cy, x0, y0, cw, ch);
+    if (min(y0 + ch, G.row_end) <= max(y0, G.row_begin)) return; // not queued: its slot entry is stale
+    const uint32_t slot = args.cell_slot[cell];
+    if (slot == NO_SLOT) return;
+    const uint32_t lid = cell_list_id(cx, cy);
+    const uint32_t items = cell_items(list_off[lid + 1] - list_off[lid], cell);
+    float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t k = 0; k < items; ++k)
+    {
+        const float4 p = args.partial[(size_t)(slot + k) * 32 + lane];
+        L.x += p.x; L.y += p.y; L.z += p.z; L.w += p.w;
+    }
+    const int lx = lane & (CELL_W - 1), ly = lane >> 3;
+    const int px = x0 + lx, py = y0 + ly;
+    if (lx < cw && ly < ch && py >= G.row_begin && py < G.row_end) store_pixel(args, (size_t)py * G.W + px, L.x, L.y, L.z, L.w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1148,7 +1208,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
         if (lane == 0) qi = atomicAdd(args.counter + 1, 1u) + queue_begin;
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= args.n_queue) break;
-        const uint32_t cell = args.queue[qi];
+        const uint32_t cell = args.queue[qi] & ((1u << ITEM_CELL_BITS) - 1u); // (lists this short are never split)
         const int cx = cell % G.ncx, cy = cell / G.ncx;
         int x0, y0, cw, ch;
         cell_rect(cx, cy, x0, y0, cw, ch);
@@ -1432,7 +1492,7 @@ struct vrt_cuda_ctx
     DevBuf cullrec;    // reference tiling projection
     DevBuf lvl_counts[4], lvl_offsets[4], lvl_idx[4], lvl_group_off; // coarse culling levels
     DevBuf ccounts, coffsets, cidx;       // level 1 (cells / tiles)
-    DevBuf hist, queue, stats, counter, rowcost, scan_tmp;
+    DevBuf hist, queue, stats, counter, rowcost, scan_tmp, cell_slot, partial;
     DevBuf out_image, out_rad;
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
     DevBuf tile_off;
@@ -1441,7 +1501,7 @@ struct vrt_cuda_ctx
     bool have_lists = false;
     bool lists_from_host = false;
     bool lists_sorted = false;
-    uint32_t n_big = 0;
+    uint32_t n_big = 0, n_split = 0;
     bool win_attr[2] = {false, false};
     FrameGeom geom{};
     uint32_t n_lists = 0;
@@ -1622,7 +1682,6 @@ int build_queue(vrt_cuda_ctx *ctx)
     ctx->cy_end = cye;
     const int ncells = (cye - cyb) * G.ncx;
     if (int rc = reserve(ctx, ctx->hist, sizeof(uint32_t) * 65536)) return rc;
-    if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max(ncells, 1))) return rc;
     if (int rc = reserve(ctx, ctx->stats, sizeof(TileStats))) return rc;
     if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
     if (int rc = reserve(ctx, ctx->rowcost, sizeof(double) * (size_t)G.ncy)) return rc;
@@ -1634,20 +1693,21 @@ int build_queue(vrt_cuda_ctx *ctx)
     k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(loff, ctx->n_lists, (TileStats *)ctx->stats.p);
     k1_hist<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
     k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p);
-    // descending order: the start slot of key WIN_CAP = number of cells with a longer list (they lead the queue)
+    // descending order: the start slot of key WIN_CAP = number of items with a longer list (they lead the queue)
     CU(cudaMemcpyAsync(&((TileStats *)ctx->stats.p)->n_big, (const uint32_t *)ctx->hist.p + WIN_CAP, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    k1_order<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, cyb, cye);
+    // the queue holds one item per cell plus the extra slices of split cells: size it from the counts k1_hist produced
+    TileStats ts;
+    CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->n_queue = (uint32_t)ts.n_items;
+    ctx->n_split = (uint32_t)ts.n_split;
+    ctx->n_big = (uint32_t)ts.n_big;
+    if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max<uint32_t>(ctx->n_queue, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->cell_slot, sizeof(uint32_t) * (size_t)G.ncx * G.ncy)) return rc;
+    CU(cudaMemsetAsync((uint32_t *)ctx->counter.p + 2, 0, sizeof(uint32_t), ctx->stream));
+    k1_order<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye);
     ctx->launches += 4;
     CU(cudaGetLastError());
-    // number of queued cells = cells with at least one band pixel
-    uint32_t nq = 0;
-    for (int cy = cyb; cy < cye; ++cy)
-    {
-        const int y0 = (cy / G.cpty) * G.tile_h + (cy % G.cpty) * CELL_H;
-        const int h = std::min(CELL_H, G.tile_h - (cy % G.cpty) * CELL_H);
-        if (std::min(y0 + h, G.row_end) > std::max(y0, G.row_begin)) nq += (uint32_t)G.ncx;
-    }
-    ctx->n_queue = nq;
     return 0;
 }
 
@@ -1765,7 +1825,7 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
-                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
+                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 4; ++i)
@@ -2031,11 +2091,6 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
-    {
-        unsigned long long nb = 0;
-        CU(cudaMemcpy(&nb, &((TileStats *)ctx->stats.p)->n_big, sizeof(nb), cudaMemcpyDeviceToHost));
-        ctx->n_big = (uint32_t)nb;
-    }
     ctx->have_lists = true;
     return 0;
 }
@@ -2161,6 +2216,10 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.terms_exec = &((TileStats *)ctx->stats.p)->terms_exec;
     a.terms_sat = &((TileStats *)ctx->stats.p)->terms_sat;
     a.window = ((frame->flags & VRT_CUDA_DEPTH_WINDOW) && a.list_idx != nullptr) ? 1u : 0u;
+    a.cell_slot = (const uint32_t *)ctx->cell_slot.p;
+    if (ctx->n_split)
+        if (int rc = reserve(ctx, ctx->partial, (size_t)ctx->n_split * 32 * sizeof(float4))) return rc;
+    a.partial = (float4 *)ctx->partial.p;
     const bool bounded = G.use_bound != 0;
     a.skip_thresh = (frame->flags & VRT_CUDA_NO_SKIP) ? -1.f : (bounded ? std::exp2(-0.5f * G.bound_k * G.bound_k * LOG2E) : 0.f);
     a.quant_nearest = (frame->flags & VRT_CUDA_QUANT_NEAREST) ? 1u : 0u;
@@ -2170,6 +2229,12 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     int rc = ((frame->flags & VRT_CUDA_ERF_MASK) == VRT_CUDA_ERF_EXACT) ? dispatch_k2<1>(ctx, a) : dispatch_k2<0>(ctx, a);
     if (rc) return rc;
+    if (ctx->n_split)
+    {
+        const uint32_t ncells = (uint32_t)((ctx->cy_end - ctx->cy_begin) * G.ncx);
+        k3_combine<<<(unsigned)(((uint64_t)ncells * 32 + 255) / 256), 256, 0, ctx->stream>>>(a, (const uint32_t *)ctx->coffsets.p, ctx->cy_begin, ctx->cy_end);
+        ctx->launches++;
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     if (stats)

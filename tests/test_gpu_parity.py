@@ -462,6 +462,28 @@ def test_config5_full_size(pkg, renderer):
     assert err_ref > err  # the reference's own fp32 evaluation is farther from the arbiter
 
 
+def test_config2_teapot_1024(pkg, renderer):
+    """BASELINE config 2 (teapot.obj as 3644 Gaussians, 1024x1024, 16 tiles): the production lists (reference AND 6 sigma)
+    against the reference's scalar path on the pixel's LITERAL reference-tile list (n ~ 370..1925), A&S and exact erf."""
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, "teapot_gaussians.npy"))
+    W = 1024
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    rng = np.random.default_rng(2)
+    # pixels on the teapot's footprint (centre half of the frame) plus a few anywhere
+    pix = np.unique(np.concatenate([(rng.integers(256, 768, 14) * W + rng.integers(256, 768, 14)), rng.integers(0, W * W, 4)]).astype(np.uint64))
+    lists = reference_lists(scene, cam.view_matrix, 16)
+    for mode, variant in (("MODE8", 1), ("MODE5", 0)):
+        flags = (getattr(V, mode) & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+        f = renderer.frame(cam.view_matrix, origin, W, W, flags, (16, 16), 6.0)
+        _, rad, st = renderer.frame_render(f, False, True)
+        ref = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, variant, tiles=16, lists=lists)
+        check(gpu_at(rad, pix, W), ref, f"config2 teapot 1024^2 {mode}: bounded lists vs literal reference lists")
+        print(f"  listed {st['terms_listed']:.3e} (reference lists: 1.0e13, SURVEY.md 8(d)), render {st['ms_render']:.2f} ms, tile {st['ms_tile']:.2f} ms")
+        assert st["terms_listed"] < 1.0e13 / 20
+
+
 def test_config3_grid64_subsample(pkg, renderer):
     """BASELINE config 3 (64x64 grid, 2048^2, 16 tiles): bounded lists on the GPU vs the reference's scalar path on the pixel's
     literal reference-tile list (n ~ 1600) for a handful of pixels inside the grid's footprint."""
