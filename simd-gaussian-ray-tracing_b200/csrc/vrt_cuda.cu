@@ -40,9 +40,9 @@ __host__ __device__ constexpr int k2_cta_warps(int q, int minb) { return (q == 8
 constexpr int STAGE = 32;          // records staged per warp per step (one per lane)
 constexpr int WIN_CAP = 160;       // longest list the depth-window kernel caches per warp ((WIN_CAP+1) * 128 B of prefix sums)
 // Heavy cells (work ~ n^2) are split by emitter range into independent work items so one warp never owns a whole long list:
-// a cell with more than SPLIT_MIN entries becomes ceil(n / SLICE) items; the partial radiances are summed in slice order.
-constexpr int SPLIT_MIN = 192;
-constexpr int SLICE = 64;          // emitters per item of a split cell (a multiple of every emitter block size Q)
+// a cell with more than 3 x slice entries becomes ceil(n / slice) items; the partial radiances are summed in slice order.
+constexpr int SLICE_MAX = 64;      // emitters per item of a split cell: 64 on big frames, down to 8 when a frame has too few
+constexpr int SLICE_MIN = 8;       //   items to fill the machine (always a multiple of every emitter block size Q)
 constexpr int ITEM_CELL_BITS = 22; // work item = cell id | slice << 22  (4M cells, 1024 slices)
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
@@ -62,6 +62,7 @@ struct FrameGeom
     int cptx, cpty;   // cells per tile
     int ncx, ncy;     // global cell grid
     int row_begin, row_end;
+    int slice;        // emitters per work item of a split cell (build_queue picks it per frame); cells with <= 3 slice entries stay whole
     int uniform;      // every tile is a whole number of cells and cells tile the image exactly: cell (cx, cy) starts at (8 cx, 4 cy)
     // list semantics
     int use_ref;      // apply the reference predicate
@@ -667,11 +668,14 @@ __device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int 
 // number of work items of a cell with an n-entry list
 __device__ __forceinline__ uint32_t cell_items(uint32_t n, uint32_t cell)
 {
-    if (n <= (uint32_t)SPLIT_MIN || cell >= (1u << ITEM_CELL_BITS)) return 1u;
-    const uint32_t k = (n + SLICE - 1) / SLICE;
+    const uint32_t slice = (uint32_t)c_geom.slice;
+    if (n <= 3u * slice || cell >= (1u << ITEM_CELL_BITS)) return 1u;
+    const uint32_t k = (n + slice - 1) / slice;
     return k <= (1u << (32 - ITEM_CELL_BITS)) ? k : 1u;
 }
 
+// COUNT_ITEMS = false: listed terms and per-row cost; true: work items per list-length key (needs c_geom.slice)
+template <bool COUNT_ITEMS>
 __global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
                         double *__restrict__ row_cost, int cy_begin, int cy_end)
 {
@@ -689,17 +693,26 @@ __global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restr
         const uint32_t n = list_off[id + 1] - list_off[id];
         if (yb > ya)
         {
-            terms = 5.0 * (double)n * (double)n * (double)(w * (yb - ya));
-            const uint32_t items = cell_items(n, (uint32_t)(cy * G.ncx + cx));
-            atomicAdd(&hist[min(n, 65535u)], items);
-            atomicAdd(&stats->n_items, (unsigned long long)items);
-            if (items > 1) atomicAdd(&stats->n_split, (unsigned long long)items);
-            if (row_cost != nullptr) atomicAdd(&row_cost[cy], terms);
+            if (COUNT_ITEMS)
+            {
+                const uint32_t items = cell_items(n, (uint32_t)(cy * G.ncx + cx));
+                atomicAdd(&hist[min(n, 65535u)], items);
+                atomicAdd(&stats->n_items, (unsigned long long)items);
+                if (items > 1) atomicAdd(&stats->n_split, (unsigned long long)items);
+            }
+            else
+            {
+                terms = 5.0 * (double)n * (double)n * (double)(w * (yb - ya));
+                if (row_cost != nullptr) atomicAdd(&row_cost[cy], terms);
+            }
         }
     }
-    // block reduction of terms
-    for (int o = 16; o > 0; o >>= 1) terms += __shfl_xor_sync(0xffffffffu, terms, o);
-    if ((threadIdx.x & 31) == 0 && terms != 0.0) atomicAdd(&stats->terms_listed, terms);
+    if (!COUNT_ITEMS)
+    {
+        // warp reduction of the listed terms
+        for (int o = 16; o > 0; o >>= 1) terms += __shfl_xor_sync(0xffffffffu, terms, o);
+        if ((threadIdx.x & 31) == 0 && terms != 0.0) atomicAdd(&stats->terms_listed, terms);
+    }
 }
 
 __global__ void k1_list_stats(const uint32_t *__restrict__ list_off, uint32_t n_lists, TileStats *__restrict__ stats)
@@ -992,7 +1005,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
         // a split cell's item covers the emitters [q_begin, q_end) only; every item still needs all n occluders
         const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
-        const uint32_t q_begin = slot != NO_SLOT ? slice * SLICE : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + SLICE) : n;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * (uint32_t)G.slice : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + (uint32_t)G.slice) : n;
         for (uint32_t q0 = q_begin; q0 < q_end; q0 += Q)
         {
             // emitter block
@@ -1208,7 +1221,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
         if (lane == 0) qi = atomicAdd(args.counter + 1, 1u) + queue_begin;
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= args.n_queue) break;
-        const uint32_t cell = args.queue[qi] & ((1u << ITEM_CELL_BITS) - 1u); // (lists this short are never split)
+        const uint32_t item = args.queue[qi];
+        const uint32_t cell = item & ((1u << ITEM_CELL_BITS) - 1u), slice = item >> ITEM_CELL_BITS;
         const int cx = cell % G.ncx, cy = cell / G.ncx;
         int x0, y0, cw, ch;
         cell_rect(cx, cy, x0, y0, cw, ch);
@@ -1257,7 +1271,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
         // ---- pass B ----
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
         unsigned long long exec = 0, sat = 0;
-        for (uint32_t q0 = 0; q0 < n; q0 += Q)
+        // a split cell's item covers the emitters [q_begin, q_end) only (pass A above is per item)
+        const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * (uint32_t)G.slice : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + (uint32_t)G.slice) : n;
+        for (uint32_t q0 = q_begin; q0 < q_end; q0 += Q)
         {
             float s[Q][5], acc[Q][5], wgt[Q];
             float4 alb[Q];
@@ -1266,7 +1283,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
 #pragma unroll
             for (int e = 0; e < Q; ++e)
             {
-                const bool real = q0 + e < n;
+                const bool real = q0 + e < q_end;
                 const uint32_t je = real ? q0 + e : q0;
                 const float4 a = sm.a[je], b = sm.b[je];
                 alb[e] = args.rec[args.list_idx[off + je]].c;
@@ -1292,7 +1309,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
                 }
             }
             if (!__any_sync(0xffffffffu, any_emit)) continue;
-            const uint32_t n_real = min((uint32_t)Q, n - q0);
+            const uint32_t n_real = min((uint32_t)Q, q_end - q0);
             const float Smin = warp_min_f(smin), Smax = warp_max_f(smax);
 
             // leading run of occluders entirely in front of every sample, trailing run entirely behind
@@ -1377,7 +1394,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 1) k2_window(const RenderArgs a
                 La = fmaf(alb[e].w, inner, La);
             }
         }
-        if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
+        else if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
         if (lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
     }
@@ -1595,6 +1613,7 @@ int make_geom(vrt_cuda_ctx *ctx, const vrt_cuda_frame *f, int list_kind_override
     G.ncx = G.tiles_x * G.cptx;
     G.ncy = G.tiles_y * G.cpty;
     G.uniform = (G.tile_w % CELL_W == 0 && G.tile_h % CELL_H == 0) ? 1 : 0;
+    G.slice = SLICE_MAX;
     G.row_begin = (int)f->row_begin;
     G.row_end = (int)f->row_end;
     if (f->row_begin == 0 && f->row_end == 0) G.row_end = G.H;
@@ -1691,12 +1710,24 @@ int build_queue(vrt_cuda_ctx *ctx)
     const uint32_t *loff = (const uint32_t *)ctx->coffsets.p;
     const int tb = 256, gb = (ncells + tb - 1) / tb;
     k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(loff, ctx->n_lists, (TileStats *)ctx->stats.p);
-    k1_hist<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
+    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
+    TileStats ts;
+    CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    {
+        // Slice size of split cells: as large as possible (every item repeats pass A), but no item may exceed a quarter of
+        // the average work per resident warp, or the longest lists would decide the frame time on small frames.
+        const double per_warp = ts.terms_listed / ((double)ctx->sm_count * 12.0);
+        int slice = SLICE_MAX;
+        while (slice > SLICE_MIN && 160.0 * slice * (double)ts.max_list > per_warp / 4.0) slice /= 2;
+        ctx->geom.slice = slice;
+        CU(cudaMemcpyToSymbolAsync(c_geom, &ctx->geom, sizeof(FrameGeom), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, nullptr, cyb, cye);
     k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p);
     // descending order: the start slot of key WIN_CAP = number of items with a longer list (they lead the queue)
     CU(cudaMemcpyAsync(&((TileStats *)ctx->stats.p)->n_big, (const uint32_t *)ctx->hist.p + WIN_CAP, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     // the queue holds one item per cell plus the extra slices of split cells: size it from the counts k1_hist produced
-    TileStats ts;
     CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n_queue = (uint32_t)ts.n_items;
@@ -1706,7 +1737,7 @@ int build_queue(vrt_cuda_ctx *ctx)
     if (int rc = reserve(ctx, ctx->cell_slot, sizeof(uint32_t) * (size_t)G.ncx * G.ncy)) return rc;
     CU(cudaMemsetAsync((uint32_t *)ctx->counter.p + 2, 0, sizeof(uint32_t), ctx->stream));
     k1_order<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CU(cudaGetLastError());
     return 0;
 }
