@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VRT_CUDA_ABI_VERSION 2
+#define VRT_CUDA_ABI_VERSION 3
 
 /* Error codes */
 #define VRT_CUDA_OK 0
@@ -68,6 +68,30 @@ extern "C" {
  * of 5Q full terms.  Same image (sums are reordered: differences ~1e-7), several times fewer evaluated terms;
  * vrt_cuda_stats.terms_saturated counts the terms resolved that way. */
 #define VRT_CUDA_DEPTH_WINDOW (1u << 7)
+
+/* The reference's alternative approximations as selectable device functions (src/vrt/approx.h:10-46; the template
+ * arguments <Exp, Erf> of the render entries, src/vrt/rt.h:315, 344, exercised by tests/img-error.cpp:40-43).
+ * An erf selection overrides the ERF_AS / ERF_EXACT bit.  Exp replaces the exponential of c_bar and of the final
+ * exp(T) (rt.h:115, 126); the density at the sample points keeps the exact exponential, as in the reference
+ * (rt.h:218 uses the pdf's template default).  These run on a plain kernel without the saturation / sign shortcuts
+ * (the approximations are neither odd nor continuous) and cannot be combined with VRT_CUDA_DEPTH_WINDOW. */
+#define VRT_CUDA_APPROX_ERF_SPLINE (1u << 8)         /* approx::spline_erf,        approx.cpp:9-23   */
+#define VRT_CUDA_APPROX_ERF_SPLINE_MIRROR (2u << 8)  /* approx::spline_erf_mirror, approx.cpp:45-56  */
+#define VRT_CUDA_APPROX_ERF_TAYLOR (3u << 8)         /* approx::taylor_erf,        approx.cpp:64-77  */
+#define VRT_CUDA_APPROX_ERF_MASK (3u << 8)
+#define VRT_CUDA_APPROX_EXP_FAST (1u << 10)          /* approx::simd_fast_exp,     approx.cpp:112-137 (range-clamped) */
+#define VRT_CUDA_APPROX_EXP_SPLINE (2u << 10)        /* approx::spline_exp,        approx.cpp:141-163 */
+#define VRT_CUDA_APPROX_EXP_MASK (3u << 10)
+
+/* Function ids of vrt_cuda_approx_table(): the columns of tests/accuracy.cpp's erf.csv / exp.csv. */
+#define VRT_CUDA_FN_SPLINE_ERF 0
+#define VRT_CUDA_FN_SPLINE_ERF_MIRROR 1
+#define VRT_CUDA_FN_TAYLOR_ERF 2
+#define VRT_CUDA_FN_AS_ERF 3
+#define VRT_CUDA_FN_ERF 4        /* the device's libm-class erf (VRT_CUDA_ERF_EXACT) */
+#define VRT_CUDA_FN_EXP 5        /* the device's exp (MUFU.EX2)                      */
+#define VRT_CUDA_FN_FAST_EXP 6
+#define VRT_CUDA_FN_SPLINE_EXP 7
 
 /* Flag sets reproducing the reference's modes (src/volumetric-ray-tracer/main.cpp:150-177). */
 #define VRT_CUDA_MODE1 (VRT_CUDA_ERF_EXACT | VRT_CUDA_LIST_ALL | VRT_CUDA_QUANT_TRUNCATE | VRT_CUDA_ALPHA_OPAQUE)
@@ -179,6 +203,10 @@ int vrt_cuda_term_peak(vrt_cuda_ctx *ctx, int pairs, int ctas_per_sm, double *te
 
 /* Pipe-mix probe: chain steps/s where one step = nf FFMA2 + nm MUFU.RCP + nl LOP3 (a few fixed combinations). */
 int vrt_cuda_mix_peak(vrt_cuda_ctx *ctx, int nf, int nm, int nl, double *steps_per_s_out);
+
+/* y[i] = f(x[i]) for one of the VRT_CUDA_FN_* device functions, evaluated on the GPU (host pointers): the drop-in for the
+ * tabulation loops of tests/accuracy.cpp:16-52, and the way the parity tests pin every device approximation. */
+int vrt_cuda_approx_table(vrt_cuda_ctx *ctx, int fn, const float *x, float *y, uint64_t n);
 
 int vrt_cuda_sync(vrt_cuda_ctx *ctx);
 /* The context's cudaStream_t as an integer (for ordering NCCL / torch work after a render_device). */

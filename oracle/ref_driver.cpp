@@ -11,6 +11,8 @@
 //   vrt::render_image / vrt::simd_render_image  src/vrt/rt.h:227-404
 //   vrt::camera_t                               src/vrt/camera.cpp:7-71
 //   vrt::approx::abramowitz_stegun_erf          src/vrt/approx.cpp:90-99
+//   vrt::approx::{spline_erf, spline_erf_mirror, taylor_erf, fast_exp, spline_exp} and their simd_ forms
+//                                               src/vrt/approx.h:10-46
 //   read_from_obj                               src/vrt/gaussians-from-file.cpp:7-44
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
@@ -58,13 +60,76 @@ namespace
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     }
 
+    // Variant code = erf id | exp id << 4 (same coding as oracle/vrt_oracle.c):
+    //   erf 0 libm erff (scalar default, rt.h:32)  1 abramowitz_stegun_erf  2 spline_erf  3 spline_erf_mirror  4 taylor_erf
+    //   exp 0 libm expf                            1 fast_exp               2 spline_exp         (src/vrt/approx.h:10-46)
     typedef vec4f_t (*rad_fn)(const vec4f_t, const vec4f_t, const gaussians_t &);
+    typedef f32 (*tr_fn)(const vec4f_t, const vec4f_t, const f32, const gaussians_t &);
+    template <f32_func_t Exp>
+    rad_fn pick_radiance_erf(int erf_id)
+    {
+        switch (erf_id)
+        {
+        case 1: return radiance<transmittance<Exp, approx::abramowitz_stegun_erf>>;
+        case 2: return radiance<transmittance<Exp, approx::spline_erf>>;
+        case 3: return radiance<transmittance<Exp, approx::spline_erf_mirror>>;
+        case 4: return radiance<transmittance<Exp, approx::taylor_erf>>;
+        default: return radiance<transmittance<Exp, erff>>;
+        }
+    }
     rad_fn pick_radiance(int variant)
     {
-        // 0: libm expf + libm erff (the reference's scalar default, rt.h:32)
-        // 1: libm expf + Abramowitz-Stegun erf (scalar path, same erf as modes 4/8)
-        if (variant == 1) return radiance<transmittance<expf, approx::abramowitz_stegun_erf>>;
-        return radiance<transmittance<expf, erff>>;
+        switch ((variant >> 4) & 15)
+        {
+        case 1: return pick_radiance_erf<approx::fast_exp>(variant & 15);
+        case 2: return pick_radiance_erf<approx::spline_exp>(variant & 15);
+        default: return pick_radiance_erf<expf>(variant & 15);
+        }
+    }
+    template <f32_func_t Exp>
+    tr_fn pick_transmittance_erf(int erf_id)
+    {
+        switch (erf_id)
+        {
+        case 1: return transmittance<Exp, approx::abramowitz_stegun_erf>;
+        case 2: return transmittance<Exp, approx::spline_erf>;
+        case 3: return transmittance<Exp, approx::spline_erf_mirror>;
+        case 4: return transmittance<Exp, approx::taylor_erf>;
+        default: return transmittance<Exp, erff>;
+        }
+    }
+    tr_fn pick_transmittance(int variant)
+    {
+        switch ((variant >> 4) & 15)
+        {
+        case 1: return pick_transmittance_erf<approx::fast_exp>(variant & 15);
+        case 2: return pick_transmittance_erf<approx::spline_exp>(variant & 15);
+        default: return pick_transmittance_erf<expf>(variant & 15);
+        }
+    }
+
+    // tiled SIMD render entry (rt.h:344-404) with the SIMD forms of the same approximations; exact erf has no SIMD form
+    // without SVML, so erf id 0 maps to simd::erf (= Abramowitz-Stegun, approx.h:110-118)
+    typedef bool (*simd_render_fn)(const u32, const u32, u32 *, const camera_t &, const vec4f_t, const tiles_t &, const bool &, const u64);
+    template <simd_f32_func_t Exp>
+    simd_render_fn pick_simd_render_erf(int erf_id)
+    {
+        switch (erf_id)
+        {
+        case 2: return simd_render_image<Exp, approx::simd_spline_erf>;
+        case 3: return simd_render_image<Exp, approx::simd_spline_erf_mirror>;
+        case 4: return simd_render_image<Exp, approx::simd_taylor_erf>;
+        default: return simd_render_image<Exp, approx::simd_abramowitz_stegun_erf>;
+        }
+    }
+    simd_render_fn pick_simd_render(int variant)
+    {
+        switch ((variant >> 4) & 15)
+        {
+        case 1: return pick_simd_render_erf<approx::simd_fast_exp>(variant & 15);
+        case 2: return pick_simd_render_erf<approx::simd_spline_exp>(variant & 15);
+        default: return pick_simd_render_erf<approx::vcl_exp<sizeof(simd::Vec<simd::Float>)>>(variant & 15);
+        }
     }
 }
 
@@ -163,13 +228,84 @@ extern "C"
         const vec4f_t o{origin4[0], origin4[1], origin4[2], origin4[3]};
         const vec4f_t d{dir4[0], dir4[1], dir4[2], dir4[3]};
         for (u64 k = 0; k < n_s; ++k)
-            T_out[k] = (variant == 1) ? transmittance<expf, approx::abramowitz_stegun_erf>(o, d, s[k], gs)
-                                      : transmittance<expf, erff>(o, d, s[k], gs);
+            T_out[k] = pick_transmittance(variant)(o, d, s[k], gs);
     }
 
     void ref_as_erf(const float *x, uint64_t n, float *y)
     {
         for (u64 i = 0; i < n; ++i) y[i] = approx::abramowitz_stegun_erf(x[i]);
+    }
+
+    /// The functions tests/accuracy.cpp tabulates (src/vrt/approx.h:10-46).  fn 0 spline_erf, 1 spline_erf_mirror, 2 taylor_erf,
+    /// 3 abramowitz_stegun_erf, 4 erff, 5 expf, 6 fast_exp, 7 spline_exp; fn + 16 = the SIMD form of the same function
+    /// (erff/expf have none: 4+16 -> simd::erf, 5+16 -> vcl_exp).  Returns 0, or -1 for an unknown fn.
+    int ref_approx_table(int fn, const float *x, uint64_t n, float *y)
+    {
+        if (fn < 16)
+        {
+            f32_func_t f = nullptr;
+            switch (fn)
+            {
+            case 0: f = approx::spline_erf; break;
+            case 1: f = approx::spline_erf_mirror; break;
+            case 2: f = approx::taylor_erf; break;
+            case 3: f = approx::abramowitz_stegun_erf; break;
+            case 4: f = erff; break;
+            case 5: f = expf; break;
+            case 6: f = approx::fast_exp; break;
+            case 7: f = approx::spline_exp; break;
+            default: return -1;
+            }
+            for (u64 i = 0; i < n; ++i) y[i] = f(x[i]);
+            return 0;
+        }
+        simd_f32_func_t f = nullptr;
+        switch (fn - 16)
+        {
+        case 0: f = approx::simd_spline_erf; break;
+        case 1: f = approx::simd_spline_erf_mirror; break;
+        case 2: f = approx::simd_taylor_erf; break;
+        case 3: f = approx::simd_abramowitz_stegun_erf; break;
+        case 4: f = simd::erf; break;
+        case 5: f = approx::vcl_exp<sizeof(simd::Vec<simd::Float>)>; break;
+        case 6: f = approx::simd_fast_exp; break;
+        case 7: f = approx::simd_spline_exp; break;
+        default: return -1;
+        }
+        for (u64 i = 0; i < n; i += SIMD_FLOATS)
+        {
+            f32 in[SIMD_FLOATS], out[SIMD_FLOATS];
+            for (u64 k = 0; k < SIMD_FLOATS; ++k) in[k] = x[i + k < n ? i + k : n - 1];
+            simd::storeu(out, f(simd::loadu(in)));
+            for (u64 k = 0; k < SIMD_FLOATS && i + k < n; ++k) y[i + k] = out[k];
+        }
+        return 0;
+    }
+
+    /// The procedure of tests/img-error.cpp:27-43 for one SIMD variant: lists from tile_gaussians(tw, tw, scene, tiling_view),
+    /// default camera_create_info_t camera (position 0, yaw -90, 256x256, focal 1), origin 0, tiled SIMD entry
+    /// simd_render_image<Exp, Erf> (variant >= 0) or the scalar reference image render_image<radiance<transmittance>>
+    /// (variant < 0, img-error.cpp:34).  image_out: w*h packed pixels.
+    int ref_img_error_image(const float *aos, uint64_t n, float tw, const float *tiling_view16, uint64_t w, uint64_t h,
+                            uint64_t threads, int variant, uint32_t *image_out)
+    {
+        std::vector<gaussian_t> g = from_aos(aos, n);
+        glm::mat4 view;
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) view[j][i] = tiling_view16[4 * j + i];
+        tiles_t tiles = tile_gaussians(tw, tw, g, view);
+        camera_create_info_t ci{};
+        ci.width = w;
+        ci.height = h;
+        const camera_t cam(ci);
+        const vec4f_t origin{0.f, 0.f, 0.f};
+        u32 *image = (u32 *)simd::aligned_malloc(sizeof(u32) * w * h);
+        const bool running = true;
+        if (variant < 0) render_image<radiance<transmittance>>(w, h, image, cam, origin, tiles, running, threads);
+        else pick_simd_render(variant)(w, h, image, cam, origin, tiles, running, threads);
+        std::memcpy(image_out, image, sizeof(u32) * w * h);
+        simd::aligned_free(image);
+        return 0;
     }
 
     /// The app's frame (main.cpp:257-297) for one mode: tile_gaussians + the mode's render entry.

@@ -54,9 +54,169 @@ static double as_erf_f64(double x)
     return (1.0 - 1.0 / (denom2 * denom2)) * sign;
 }
 
-/* variant 0: libm expf/erff (template defaults, src/vrt/rt.h:32); variant 1: expf + A&S erf. */
-static inline float erf_variant_f32(int variant, float x) { return variant == 1 ? orc_as_erf_f32(x) : erff(x); }
-static inline double erf_variant_f64(int variant, double x) { return variant == 1 ? as_erf_f64(x) : erf(x); }
+/* ---------------------------------------------------------------- alternative approximations */
+#include "../include/vrt_approx_tables.h"
+
+/* Piecewise-cubic lookup shared by spline_erf (src/vrt/approx.cpp:9-23) and spline_exp (:141-163):
+ * x <= first knot -> `below`, x >= last knot -> `above`, else the segment whose half-open interval holds x. */
+static float spline_f32(const float *knot, const float (*coef)[4], int nseg, float below, float above, float x)
+{
+    if (x <= knot[0]) return below;
+    for (int i = 0; i < nseg; ++i)
+        if (x < knot[i + 1])
+        {
+            const float d = x - knot[i];
+            return ((coef[i][0] * d + coef[i][1]) * d + coef[i][2]) * d + coef[i][3];
+        }
+    return above;
+}
+static double spline_f64(const float *knot, const float (*coef)[4], int nseg, double below, double above, double x)
+{
+    if (x <= (double)knot[0]) return below;
+    for (int i = 0; i < nseg; ++i)
+        if (x < (double)knot[i + 1])
+        {
+            const double d = x - (double)knot[i];
+            return (((double)coef[i][0] * d + (double)coef[i][1]) * d + (double)coef[i][2]) * d + (double)coef[i][3];
+        }
+    return above;
+}
+
+ORC_API float orc_spline_erf_f32(float x) { return spline_f32(vrt_spline_erf_knot, vrt_spline_erf_coef, VRT_SPLINE_ERF_SEGMENTS, -1.f, 1.f, x); }
+ORC_API float orc_spline_exp_f32(float x) { return spline_f32(vrt_spline_exp_knot, vrt_spline_exp_coef, VRT_SPLINE_EXP_SEGMENTS, 0.f, 1.f, x); }
+
+/* src/vrt/approx.cpp:45-56: the negative half of the erf spline (segments 0..3, then segment 4 for everything up to 0)
+ * evaluated at -|x| and mirrored; SIGN(0) = +1 there (approx.cpp:5). */
+ORC_API float orc_spline_erf_mirror_f32(float x)
+{
+    const float sign = (float)((x >= 0) - (x < 0));
+    const float m = -sign * x; /* -|x| */
+    if (m <= vrt_spline_erf_knot[0]) return sign;
+    int i = 0;
+    while (i < 4 && !(m < vrt_spline_erf_knot[i + 1])) ++i;
+    const float d = m - vrt_spline_erf_knot[i];
+    const float v = ((vrt_spline_erf_coef[i][0] * d + vrt_spline_erf_coef[i][1]) * d + vrt_spline_erf_coef[i][2]) * d + vrt_spline_erf_coef[i][3];
+    return -sign * v;
+}
+static double spline_erf_mirror_f64(double x)
+{
+    const double sign = (double)((x >= 0) - (x < 0));
+    const double m = -sign * x;
+    if (m <= (double)vrt_spline_erf_knot[0]) return sign;
+    int i = 0;
+    while (i < 4 && !(m < (double)vrt_spline_erf_knot[i + 1])) ++i;
+    const double d = m - (double)vrt_spline_erf_knot[i];
+    const double v = (((double)vrt_spline_erf_coef[i][0] * d + (double)vrt_spline_erf_coef[i][1]) * d + (double)vrt_spline_erf_coef[i][2]) * d + (double)vrt_spline_erf_coef[i][3];
+    return -sign * v;
+}
+
+/* src/vrt/approx.cpp:68-77: ten terms of the Maclaurin series of erf, coefficients (-1)^n / (n! (2n+1)) as fp32,
+ * saturated to +-1 outside (-2, 2). */
+static const double taylor_den[10] = {1.0, -3.0, 10.0, -42.0, 216.0, -1320.0, 9360.0, -75600.0, 685440.0, -6894720.0};
+static const float TWO_INV_SQRTPI_F = 2.f * 0.5641895835477563f;
+ORC_API float orc_taylor_erf_f32(float x)
+{
+    if (x <= -2.f) return -1.f;
+    if (x >= 2.f) return 1.f;
+    float p = (float)(1.0 / taylor_den[9]);
+    for (int n = 8; n >= 0; --n) p = p * x * x + (float)(1.0 / taylor_den[n]);
+    return TWO_INV_SQRTPI_F * p * x;
+}
+static double taylor_erf_f64(double x)
+{
+    if (x <= -2.0) return -1.0;
+    if (x >= 2.0) return 1.0;
+    double p = (double)(float)(1.0 / taylor_den[9]);
+    for (int n = 8; n >= 0; --n) p = p * x * x + (double)(float)(1.0 / taylor_den[n]);
+    return (double)TWO_INV_SQRTPI_F * p * x;
+}
+
+/* src/vrt/approx.cpp:112-127, Schraudolph's exp: the float a x + b, converted to an integer, IS the bit pattern of the
+ * result.  The range clamp is the one the reference compiles in unless NDEBUG is defined (its CMake build does not define
+ * it); outside [2^23, 255 * 2^23] the unclamped conversion is undefined behaviour, so the clamp is the only definition.
+ * The scalar function truncates, the SIMD one (:130-137, cvts) rounds to nearest: `nearest` selects. */
+static float fast_exp_impl(float x, int nearest)
+{
+    const float a = (float)(1 << 23) / 0.6931471805599453f;
+    const float b = (float)(1 << 23) * (127.f - 0.043677448f);
+    const float lo = (float)(1 << 23), hi = (float)(1 << 23) * 255.f;
+    float y = a * x + b;
+    if (y < lo || y > hi) y = (y < lo) ? 0.f : hi;
+    const uint32_t n = nearest ? (uint32_t)llrintf(y) : (uint32_t)y;
+    float r;
+    memcpy(&r, &n, sizeof(r));
+    return r;
+}
+ORC_API float orc_fast_exp_f32(float x) { return fast_exp_impl(x, 0); }
+ORC_API float orc_fast_exp_simd_f32(float x) { return fast_exp_impl(x, 1); }
+
+/* Variant code = erf id | exp id << 4.
+ * erf id 0: libm erff (template default, src/vrt/rt.h:32)   1: Abramowitz-Stegun   2: spline   3: mirrored spline   4: Taylor
+ * exp id 0: libm expf                                      1: fast_exp (SIMD rounding)        2: spline_exp
+ * Exp applies to c_bar and to the final exp(T) (rt.h:45, 53 / :115, 126); the density G_q(x) always uses libm exp
+ * (types.h:204-208; the SIMD pdf's template default, rt.h:218). */
+static inline float erf_variant_f32(int variant, float x)
+{
+    switch (variant & 15)
+    {
+    case 1: return orc_as_erf_f32(x);
+    case 2: return orc_spline_erf_f32(x);
+    case 3: return orc_spline_erf_mirror_f32(x);
+    case 4: return orc_taylor_erf_f32(x);
+    default: return erff(x);
+    }
+}
+static inline double erf_variant_f64(int variant, double x)
+{
+    switch (variant & 15)
+    {
+    case 1: return as_erf_f64(x);
+    case 2: return spline_f64(vrt_spline_erf_knot, vrt_spline_erf_coef, VRT_SPLINE_ERF_SEGMENTS, -1.0, 1.0, x);
+    case 3: return spline_erf_mirror_f64(x);
+    case 4: return taylor_erf_f64(x);
+    default: return erf(x);
+    }
+}
+static inline float exp_variant_f32(int variant, float x)
+{
+    switch ((variant >> 4) & 15)
+    {
+    case 1: return orc_fast_exp_simd_f32(x);
+    case 2: return orc_spline_exp_f32(x);
+    default: return expf(x);
+    }
+}
+static inline double exp_variant_f64(int variant, double x)
+{
+    switch ((variant >> 4) & 15)
+    {
+    case 1: return (double)orc_fast_exp_simd_f32((float)x); /* the bit trick is an fp32 construction */
+    case 2: return spline_f64(vrt_spline_exp_knot, vrt_spline_exp_coef, VRT_SPLINE_EXP_SEGMENTS, 0.0, 1.0, x);
+    default: return exp(x);
+    }
+}
+
+/* tabulation entry for tests (the functions tests/accuracy.cpp tabulates): fn 0 spline_erf, 1 spline_erf_mirror,
+ * 2 taylor_erf, 3 abramowitz_stegun_erf, 4 erff, 5 expf, 6 fast_exp (scalar, truncating), 7 spline_exp, 8 fast_exp (SIMD rounding) */
+ORC_API void orc_approx_table(int fn, const float *x, uint64_t n, float *y)
+{
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const float v = x[i];
+        switch (fn)
+        {
+        case 0: y[i] = orc_spline_erf_f32(v); break;
+        case 1: y[i] = orc_spline_erf_mirror_f32(v); break;
+        case 2: y[i] = orc_taylor_erf_f32(v); break;
+        case 3: y[i] = orc_as_erf_f32(v); break;
+        case 4: y[i] = erff(v); break;
+        case 5: y[i] = expf(v); break;
+        case 6: y[i] = orc_fast_exp_f32(v); break;
+        case 7: y[i] = orc_spline_exp_f32(v); break;
+        default: y[i] = orc_fast_exp_simd_f32(v); break;
+        }
+    }
+}
 
 /* ---------------------------------------------------------------- transmittance ------------- */
 
@@ -73,7 +233,7 @@ ORC_API float orc_transmittance_f32(const float *o, const float *n, float s, con
         const float mb2 = mu_bar * mu_bar;
         const float sigma = q[G_SIGMA];
         const float inv_2_sigma2 = 1.f / (2.f * sigma * sigma);
-        const float c_bar = q[G_MAG] * expf(-((oc_sqnorm - mb2) * inv_2_sigma2));
+        const float c_bar = q[G_MAG] * exp_variant_f32(variant, -((oc_sqnorm - mb2) * inv_2_sigma2));
         const float sqrt_2_sig = SQRT_2_F * sigma;
         const float mu_bar_n = mu_bar / sqrt_2_sig;
         const float s_n = s / sqrt_2_sig;
@@ -81,7 +241,7 @@ ORC_API float orc_transmittance_f32(const float *o, const float *n, float s, con
         const float erf2 = erf_variant_f32(variant, s_n - mu_bar_n);
         T += sigma * c_bar * INV_SQRT_2_PI_F * (erf1 - erf2);
     }
-    return expf(T);
+    return exp_variant_f32(variant, T);
 }
 
 static double transmittance_f64_d(const float *o, const double *n, double s, const float *g, uint64_t count, int variant)
@@ -94,13 +254,13 @@ static double transmittance_f64_d(const float *o, const double *n, double s, con
         const double mu_bar = cx * n[0] + cy * n[1] + cz * n[2] + cw * n[3];
         const double oc_sqnorm = cx * cx + cy * cy + cz * cz + cw * cw;
         const double sigma = q[G_SIGMA];
-        const double c_bar = (double)q[G_MAG] * exp(-((oc_sqnorm - mu_bar * mu_bar) / (2.0 * sigma * sigma)));
+        const double c_bar = (double)q[G_MAG] * exp_variant_f64(variant, -((oc_sqnorm - mu_bar * mu_bar) / (2.0 * sigma * sigma)));
         const double sqrt_2_sig = (double)SQRT_2_F * sigma;
         const double erf1 = erf_variant_f64(variant, -mu_bar / sqrt_2_sig);
         const double erf2 = erf_variant_f64(variant, s / sqrt_2_sig - mu_bar / sqrt_2_sig);
         T += sigma * c_bar * (double)INV_SQRT_2_PI_F * (erf1 - erf2);
     }
-    return exp(T);
+    return exp_variant_f64(variant, T);
 }
 
 ORC_API double orc_transmittance_f64(const float *o, const float *n, double s, const float *g, uint64_t count, int variant)

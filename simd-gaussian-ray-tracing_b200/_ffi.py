@@ -72,6 +72,7 @@ CUDA_SYMBOLS = {
     "vrt_cuda_fp32_peak": (c_i, [vp, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_term_peak": (c_i, [vp, c_i, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_mix_peak": (c_i, [vp, c_i, c_i, c_i, ctypes.POINTER(c_d)]),
+    "vrt_cuda_approx_table": (c_i, [vp, c_i, vp, vp, c_u64]),
     "vrt_cuda_sync": (c_i, [vp]),
     "vrt_cuda_stream": (c_u64, [vp]),
     "vrt_cuda_device": (c_i, [vp]),

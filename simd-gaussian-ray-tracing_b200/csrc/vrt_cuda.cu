@@ -14,9 +14,9 @@
 //
 // No CPU fallback: every entry point fails without a CUDA device.  Nothing under oracle/ is used here.
 #include "vrt_cuda.h"
+#include "vrt_approx_tables.h"
 
 #include <cuda_runtime.h>
-
 
 #include <algorithm>
 #include <cmath>
@@ -1178,6 +1178,244 @@ __global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, const u
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2'', the reference's alternative approximations as selectable device functions (VRT_CUDA_APPROX_*)
+// ------------------------------------------------------------------------------------------------
+// spline_erf / spline_erf_mirror / taylor_erf and fast_exp / spline_exp of src/vrt/approx.cpp plugged into the same
+// hoisted sums as k2_render, so the variant comparison of tests/img-error.cpp and the tables of tests/accuracy.cpp run on the
+// GPU.  The approximations are not odd, not monotone and (the splines) not even continuous, so none of k2_render's
+// saturation / sign shortcuts apply: this kernel evaluates every term with the selected functions, in natural-log units.
+struct ApproxTables
+{
+    float4 erf_coef[VRT_SPLINE_ERF_SEGMENTS], exp_coef[VRT_SPLINE_EXP_SEGMENTS];
+    float erf_knot[VRT_SPLINE_ERF_SEGMENTS + 1], exp_knot[VRT_SPLINE_EXP_SEGMENTS + 1];
+};
+__constant__ ApproxTables c_approx;
+
+enum { ERFV_AS = 0, ERFV_EXACT = 1, ERFV_SPLINE = 2, ERFV_SPLINE_MIRROR = 3, ERFV_TAYLOR = 4 };
+enum { EXPV_EXACT = 0, EXPV_FAST = 1, EXPV_SPLINE = 2 };
+
+// cubic of the segment [knot[i], knot[i+1]) that holds x among the first NSEG segments (x below knot[1] -> segment 0, at or
+// above knot[NSEG-1] -> the last one); the knots are read warp-uniformly, the coefficients per lane
+template <int NSEG>
+__device__ __forceinline__ float spline_segment(const float *knot, const float4 *coef, float x)
+{
+    int i = 0;
+#pragma unroll
+    for (int k = 1; k < NSEG; ++k) i += (x >= knot[k]) ? 1 : 0;
+    const float4 c = coef[i];
+    const float d = x - knot[i];
+    return fmaf(fmaf(fmaf(c.x, d, c.y), d, c.z), d, c.w);
+}
+
+template <int ERFV>
+__device__ __forceinline__ float erf_approx(const ApproxTables &T, float t)
+{
+    if (ERFV == ERFV_AS) return erf_as(t);
+    if (ERFV == ERFV_EXACT) return erf_exact(t);
+    if (ERFV == ERFV_SPLINE)
+    {
+        // src/vrt/approx.cpp:9-23: -1 up to the first knot, +1 from the last one on
+        const float v = spline_segment<VRT_SPLINE_ERF_SEGMENTS>(T.erf_knot, T.erf_coef, t);
+        return t <= T.erf_knot[0] ? -1.f : (t >= T.erf_knot[VRT_SPLINE_ERF_SEGMENTS] ? 1.f : v);
+    }
+    if (ERFV == ERFV_SPLINE_MIRROR)
+    {
+        // src/vrt/approx.cpp:45-56: the negative half (segments 0..3, then segment 4 all the way to 0) at -|t|, mirrored;
+        // sign(0) = +1
+        const float m = -fabsf(t);
+        float v = spline_segment<5>(T.erf_knot, T.erf_coef, m);
+        v = m <= T.erf_knot[0] ? -1.f : v;
+        return t >= 0.f ? -v : v;
+    }
+    // src/vrt/approx.cpp:64-77: ten Maclaurin terms (-1)^n / (n! (2n+1)), saturated outside (-2, 2)
+    const float x2 = t * t;
+    float p = -1.f / 6894720.f;
+    p = fmaf(p, x2, 1.f / 685440.f);
+    p = fmaf(p, x2, -1.f / 75600.f);
+    p = fmaf(p, x2, 1.f / 9360.f);
+    p = fmaf(p, x2, -1.f / 1320.f);
+    p = fmaf(p, x2, 1.f / 216.f);
+    p = fmaf(p, x2, -1.f / 42.f);
+    p = fmaf(p, x2, 1.f / 10.f);
+    p = fmaf(p, x2, -1.f / 3.f);
+    p = fmaf(p, x2, 1.f);
+    const float v = (2.f * 0.5641895835477563f) * p * t;
+    return t <= -2.f ? -1.f : (t >= 2.f ? 1.f : v);
+}
+
+template <int EXPV>
+__device__ __forceinline__ float exp_approx(const ApproxTables &T, float x)
+{
+    if (EXPV == EXPV_EXACT) return ex2_approx(x * LOG2E);
+    if (EXPV == EXPV_FAST)
+    {
+        // src/vrt/approx.cpp:112-137 (Schraudolph): the integer nearest to a x + b is the bit pattern of the result.  Range
+        // clamp as in the reference's non-NDEBUG build (the conversion is undefined outside it); rounding as simd::cvts.
+        constexpr float a = 8388608.f / 0.6931471805599453f, b = 8388608.f * (127.f - 0.043677448f);
+        float y = fmaf(a, x, b);
+        y = y < 8388608.f ? 0.f : fminf(y, 8388608.f * 255.f);
+        return __uint_as_float((uint32_t)__float2int_rn(y));
+    }
+    // src/vrt/approx.cpp:141-163: 0 up to the first knot, 1 from the last one (x = 0) on
+    const float v = spline_segment<VRT_SPLINE_EXP_SEGMENTS>(T.exp_knot, T.exp_coef, x);
+    return x <= T.exp_knot[0] ? 0.f : (x >= T.exp_knot[VRT_SPLINE_EXP_SEGMENTS] ? 1.f : v);
+}
+
+__device__ __forceinline__ void load_tables(ApproxTables &s_tab)
+{
+    const float *src = reinterpret_cast<const float *>(&c_approx);
+    float *dst = reinterpret_cast<float *>(&s_tab);
+    for (uint32_t i = threadIdx.x; i < sizeof(ApproxTables) / sizeof(float); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+constexpr int VQ = 4; // emitters per register block of the variant kernel
+
+template <int ERFV, int EXPV>
+__global__ void __launch_bounds__(K2_WARPS * 32) k2_variant(const RenderArgs args)
+{
+    __shared__ ApproxTables s_tab;
+    load_tables(s_tab);
+    const FrameGeom &G = c_geom;
+    const int lane = threadIdx.x & 31;
+    const int lx = lane & (CELL_W - 1), ly = lane >> 3;
+    constexpr float LN2 = 1.f / LOG2E;
+    for (;;)
+    {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(args.counter, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= args.n_queue) break;
+        const uint32_t item = args.queue[qi];
+        const uint32_t cell = item & ((1u << ITEM_CELL_BITS) - 1u), slice = item >> ITEM_CELL_BITS;
+        const int cx = cell % G.ncx, cy = cell / G.ncx;
+        int x0, y0, cw, ch;
+        cell_rect(cx, cy, x0, y0, cw, ch);
+        const int px = x0 + min(lx, cw - 1), py = y0 + min(ly, ch - 1);
+        const bool live = lx < cw && ly < ch && py >= G.row_begin && py < G.row_end;
+        const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
+        const PixelRay ray = pixel_ray(px, py);
+        const uint32_t lid = cell_list_id(cx, cy);
+        const uint32_t off = args.list_off[lid];
+        const uint32_t n = args.list_off[lid + 1] - off;
+        auto load_rec = [&](uint32_t k) -> const Rec * { return args.rec + (args.list_idx ? args.list_idx[off + k] : off + k); };
+        // occluder j for this lane: mu_bar, weight A = sigma c sqrt(pi/2) Exp(-d^2 / 2 sigma^2), r = 1/(sqrt2 sigma)
+        auto occluder = [&](const Rec *rc, float &mu, float &A, float &r) {
+            const float4 a = rc->a, b = rc->b;
+            mu = fmaf(a.z, ray.nz, fmaf(a.y, ray.ny, a.x * ray.nx));
+            const float qx = fmaf(-mu, ray.nx, a.x), qy = fmaf(-mu, ray.ny, a.y), qz = fmaf(-mu, ray.nz, a.z);
+            const float d2 = fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, a.w)));
+            A = (b.z * LN2) * exp_approx<EXPV>(s_tab, -d2 * (b.y * LN2));
+            r = b.x;
+        };
+
+        // pass A: C = sum_j A_j Erf(-m_j)
+        float C = 0.f;
+        for (uint32_t j = 0; j < n; ++j)
+        {
+            float mu, A, r;
+            occluder(load_rec(j), mu, A, r);
+            C = fmaf(A, erf_approx<ERFV>(s_tab, -mu * r), C);
+        }
+
+        // pass B
+        float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
+        unsigned long long exec = 0;
+        const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * (uint32_t)G.slice : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + (uint32_t)G.slice) : n;
+        for (uint32_t q0 = q_begin; q0 < q_end; q0 += VQ)
+        {
+            float s[VQ][5], acc[VQ][5], wgt[VQ];
+            float4 alb[VQ];
+            float s0 = 0.f;
+#pragma unroll
+            for (int e = 0; e < VQ; ++e)
+            {
+                const bool real = q0 + e < q_end;
+                const Rec *rc = load_rec(real ? q0 + e : q0);
+                const float4 b = rc->b;
+                alb[e] = rc->c;
+                float mu, ee;
+                occluder_setup(rc->a, b, ray, mu, ee);
+                if (e == 0)
+                {
+                    s0 = __shfl_sync(0xffffffffu, mu, 0);
+                    s0 = (fabsf(s0) <= 3.0e38f) ? s0 : 0.f;
+                }
+                // the density G_q at the samples always uses the exact exp (types.h:204-208; template default of the SIMD pdf)
+                wgt[e] = real ? b.z * ee * (1.f / (SQRT_PI_2 * LOG2E)) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                {
+                    s[e][k] = (mu - s0) + (float)(k - 4) * b.w;
+                    acc[e][k] = 0.f;
+                }
+            }
+            const uint32_t n_real = min((uint32_t)VQ, q_end - q0);
+            for (uint32_t j = 0; j < n; ++j)
+            {
+                float mu, A, r;
+                occluder(load_rec(j), mu, A, r);
+                // a weight of exactly 0 for the whole warp contributes exactly 0 to every sum
+                if (args.skip_thresh >= 0.f && !__any_sync(0xffffffffu, A != 0.f)) continue;
+                exec += n_real;
+                const float nm = -(mu - s0) * r;
+#pragma unroll
+                for (int e = 0; e < VQ; ++e)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                    {
+                        // two roundings, not an FMA: an emitter's own k = 0 sample must give t = 0 EXACTLY, as the reference's
+                        // s/(sqrt2 sigma) - mu_bar/(sqrt2 sigma) does -- spline_erf_mirror jumps by 0.107 across t = 0
+                        const float t = __fadd_rn(__fmul_rn(s[e][k], r), nm);
+                        acc[e][k] = fmaf(A, erf_approx<ERFV>(s_tab, t), acc[e][k]);
+                    }
+            }
+#pragma unroll
+            for (int e = 0; e < VQ; ++e)
+            {
+                float inner = 3.3546262790251185e-4f * exp_approx<EXPV>(s_tab, C - acc[e][0]);
+                inner = fmaf(1.1108996538242306e-2f, exp_approx<EXPV>(s_tab, C - acc[e][1]), inner);
+                inner = fmaf(1.3533528323661270e-1f, exp_approx<EXPV>(s_tab, C - acc[e][2]), inner);
+                inner = fmaf(6.0653065971263342e-1f, exp_approx<EXPV>(s_tab, C - acc[e][3]), inner);
+                inner += exp_approx<EXPV>(s_tab, C - acc[e][4]);
+                inner *= wgt[e];
+                Lr = fmaf(alb[e].x, inner, Lr);
+                Lg = fmaf(alb[e].y, inner, Lg);
+                Lb = fmaf(alb[e].z, inner, Lb);
+                La = fmaf(alb[e].w, inner, La);
+            }
+        }
+        if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La);
+        else if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
+    }
+}
+
+// the functions tests/accuracy.cpp tabulates, evaluated on the device
+__global__ void k_approx_table(int fn, const float *__restrict__ x, float *__restrict__ y, uint64_t n)
+{
+    __shared__ ApproxTables s_tab;
+    load_tables(s_tab);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    float r;
+    switch (fn)
+    {
+    case VRT_CUDA_FN_SPLINE_ERF: r = erf_approx<ERFV_SPLINE>(s_tab, v); break;
+    case VRT_CUDA_FN_SPLINE_ERF_MIRROR: r = erf_approx<ERFV_SPLINE_MIRROR>(s_tab, v); break;
+    case VRT_CUDA_FN_TAYLOR_ERF: r = erf_approx<ERFV_TAYLOR>(s_tab, v); break;
+    case VRT_CUDA_FN_AS_ERF: r = erf_approx<ERFV_AS>(s_tab, v); break;
+    case VRT_CUDA_FN_ERF: r = erf_approx<ERFV_EXACT>(s_tab, v); break;
+    case VRT_CUDA_FN_EXP: r = exp_approx<EXPV_EXACT>(s_tab, v); break;
+    case VRT_CUDA_FN_FAST_EXP: r = exp_approx<EXPV_FAST>(s_tab, v); break;
+    default: r = exp_approx<EXPV_SPLINE>(s_tab, v); break;
+    }
+    y[i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2', depth-window render (VRT_CUDA_DEPTH_WINDOW) for cells whose list fits the per-warp cache
 // ------------------------------------------------------------------------------------------------
 // Lists are depth-sorted by K1.  Pass A walks the list once per pixel, accumulates C and stores the per-lane PREFIX SUMS of
@@ -1526,7 +1764,7 @@ struct vrt_cuda_ctx
     uint64_t n_entries = 0;
     uint32_t n_queue = 0;
     int cy_begin = 0, cy_end = 0;
-    uint32_t launches = 0;
+    uint32_t launches = 0, render_launches = 0; // kernels of the last tile() / render()
     float ms_tile = 0.f;
     // tuning
     int tune_q = 0; // 0 = automatic: 8 emitters per register block, 4 when the lists are short
@@ -1779,7 +2017,7 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
             RenderArgs big = a;
             big.n_queue = n_big;
             launch_k2c<ERF, 8, true, 1, false, true>(ctx, big);
-            ctx->launches++;
+            ctx->render_launches++;
         }
         if (a.n_queue > n_big)
         {
@@ -1812,6 +2050,56 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     }
     return 0;
 }
+
+template <int ERFV, int EXPV>
+void launch_variant(vrt_cuda_ctx *ctx, const RenderArgs &a)
+{
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_variant<ERFV, EXPV>, K2_WARPS * 32, 0);
+    if (per_sm < 1) per_sm = 1;
+    const uint32_t want = (a.n_queue + K2_WARPS - 1) / K2_WARPS;
+    const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
+    k2_variant<ERFV, EXPV><<<grid, K2_WARPS * 32, 0, ctx->stream>>>(a);
+}
+
+template <int EXPV>
+int dispatch_variant_erf(vrt_cuda_ctx *ctx, const RenderArgs &a, int erfv)
+{
+    switch (erfv)
+    {
+    case ERFV_AS: launch_variant<ERFV_AS, EXPV>(ctx, a); break;
+    case ERFV_EXACT: launch_variant<ERFV_EXACT, EXPV>(ctx, a); break;
+    case ERFV_SPLINE: launch_variant<ERFV_SPLINE, EXPV>(ctx, a); break;
+    case ERFV_SPLINE_MIRROR: launch_variant<ERFV_SPLINE_MIRROR, EXPV>(ctx, a); break;
+    case ERFV_TAYLOR: launch_variant<ERFV_TAYLOR, EXPV>(ctx, a); break;
+    default: return fail(ctx, VRT_CUDA_E_INVALID, "unknown erf approximation %d", erfv);
+    }
+    return 0;
+}
+
+int dispatch_variant(vrt_cuda_ctx *ctx, const RenderArgs &a, int erfv, int expv)
+{
+    switch (expv)
+    {
+    case EXPV_EXACT: return dispatch_variant_erf<EXPV_EXACT>(ctx, a, erfv);
+    case EXPV_FAST: return dispatch_variant_erf<EXPV_FAST>(ctx, a, erfv);
+    case EXPV_SPLINE: return dispatch_variant_erf<EXPV_SPLINE>(ctx, a, erfv);
+    default: return fail(ctx, VRT_CUDA_E_INVALID, "unknown exp approximation %d", expv);
+    }
+}
+
+int upload_approx_tables(vrt_cuda_ctx *ctx)
+{
+    ApproxTables t{};
+    for (int i = 0; i < VRT_SPLINE_ERF_SEGMENTS; ++i)
+        t.erf_coef[i] = make_float4(vrt_spline_erf_coef[i][0], vrt_spline_erf_coef[i][1], vrt_spline_erf_coef[i][2], vrt_spline_erf_coef[i][3]);
+    for (int i = 0; i < VRT_SPLINE_EXP_SEGMENTS; ++i)
+        t.exp_coef[i] = make_float4(vrt_spline_exp_coef[i][0], vrt_spline_exp_coef[i][1], vrt_spline_exp_coef[i][2], vrt_spline_exp_coef[i][3]);
+    std::memcpy(t.erf_knot, vrt_spline_erf_knot, sizeof(t.erf_knot));
+    std::memcpy(t.exp_knot, vrt_spline_exp_knot, sizeof(t.exp_knot));
+    CU(cudaMemcpyToSymbol(c_approx, &t, sizeof(t)));
+    return 0;
+}
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -1819,6 +2107,7 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
 // ------------------------------------------------------------------------------------------------
 extern "C"
 {
+void vrt_cuda_destroy(vrt_cuda_ctx *ctx);
 int vrt_cuda_abi_version(void) { return VRT_CUDA_ABI_VERSION; }
 
 int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
@@ -1844,6 +2133,12 @@ int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
     {
         g_create_error = std::string("stream/event creation failed: ") + cudaGetErrorString(e2);
         delete c;
+        return VRT_CUDA_E_CUDA;
+    }
+    if (upload_approx_tables(c) != 0)
+    {
+        g_create_error = c->err;
+        vrt_cuda_destroy(c);
         return VRT_CUDA_E_CUDA;
     }
     *ctx_out = c;
@@ -1872,6 +2167,23 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
 const char *vrt_cuda_last_error(const vrt_cuda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int vrt_cuda_device(const vrt_cuda_ctx *ctx) { return ctx ? ctx->device : -1; }
 uint64_t vrt_cuda_stream(vrt_cuda_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+int vrt_cuda_approx_table(vrt_cuda_ctx *ctx, int fn, const float *x, float *y, uint64_t n)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (fn < 0 || fn > VRT_CUDA_FN_SPLINE_EXP) return fail(ctx, VRT_CUDA_E_INVALID, "unknown function id %d", fn);
+    if (n == 0) return 0;
+    if (!x || !y) return fail(ctx, VRT_CUDA_E_INVALID, "x / y is NULL");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = reserve(ctx, ctx->out_rad, 2 * n * sizeof(float))) return rc;
+    float *dx = (float *)ctx->out_rad.p, *dy = dx + n;
+    CU(cudaMemcpyAsync(dx, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_approx_table<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(fn, dx, dy, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(y, dy, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 int vrt_cuda_sync(vrt_cuda_ctx *ctx)
 {
@@ -2235,6 +2547,10 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         const int re = (frame->row_begin == 0 && frame->row_end == 0) ? G.H : (int)frame->row_end;
         if (rb != G.row_begin || re != G.row_end) return fail(ctx, VRT_CUDA_E_STATE, "row band differs from the tiled frame");
     }
+    const uint32_t approx_erf = frame->flags & VRT_CUDA_APPROX_ERF_MASK, approx_exp = frame->flags & VRT_CUDA_APPROX_EXP_MASK;
+    if ((approx_erf || approx_exp) && (frame->flags & VRT_CUDA_DEPTH_WINDOW))
+        return fail(ctx, VRT_CUDA_E_INVALID, "the depth window needs a saturating odd erf: not available with VRT_CUDA_APPROX_*");
+    if (approx_exp > VRT_CUDA_APPROX_EXP_SPLINE) return fail(ctx, VRT_CUDA_E_INVALID, "unknown exp approximation");
     RenderArgs a{};
     a.rec = (const Rec *)ctx->rec.p;
     a.list_off = (const uint32_t *)ctx->coffsets.p;
@@ -2258,13 +2574,21 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));
     CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_exec, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    int rc = ((frame->flags & VRT_CUDA_ERF_MASK) == VRT_CUDA_ERF_EXACT) ? dispatch_k2<1>(ctx, a) : dispatch_k2<0>(ctx, a);
+    ctx->render_launches = 1;
+    int rc;
+    if (approx_erf || approx_exp)
+    {
+        // alternative approximations: an erf selection overrides the ERF_AS / ERF_EXACT bit
+        const int erfv = approx_erf ? (int)(approx_erf >> 8) + 1 : (((frame->flags & VRT_CUDA_ERF_MASK) == VRT_CUDA_ERF_EXACT) ? ERFV_EXACT : ERFV_AS);
+        rc = dispatch_variant(ctx, a, erfv, (int)(approx_exp >> 10));
+    }
+    else rc = ((frame->flags & VRT_CUDA_ERF_MASK) == VRT_CUDA_ERF_EXACT) ? dispatch_k2<1>(ctx, a) : dispatch_k2<0>(ctx, a);
     if (rc) return rc;
     if (ctx->n_split)
     {
         const uint32_t ncells = (uint32_t)((ctx->cy_end - ctx->cy_begin) * G.ncx);
         k3_combine<<<(unsigned)(((uint64_t)ncells * 32 + 255) / 256), 256, 0, ctx->stream>>>(a, (const uint32_t *)ctx->coffsets.p, ctx->cy_begin, ctx->cy_end);
-        ctx->launches++;
+        ctx->render_launches++;
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -2278,7 +2602,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         stats->n_cells = ctx->n_lists;
         stats->list_entries = ts.entries;
         stats->max_list = (uint32_t)ts.max_list;
-        stats->n_launches = ctx->launches + 1;
+        stats->n_launches = ctx->launches + ctx->render_launches;
         stats->terms_listed = ts.terms_listed;
         stats->terms_executed = (double)ts.terms_exec;
         stats->terms_saturated = (double)ts.terms_sat;

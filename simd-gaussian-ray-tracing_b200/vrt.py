@@ -25,6 +25,10 @@ QUANT_TRUNCATE, QUANT_NEAREST = 0 << 4, 1 << 4
 ALPHA_OPAQUE, ALPHA_FROM_W = 0 << 5, 1 << 5
 NO_SKIP = 1 << 6
 DEPTH_WINDOW = 1 << 7
+# alternative approximations (src/vrt/approx.h:10-46) and the function ids of Renderer.approx_table
+APPROX_ERF_SPLINE, APPROX_ERF_SPLINE_MIRROR, APPROX_ERF_TAYLOR, APPROX_ERF_MASK = 1 << 8, 2 << 8, 3 << 8, 3 << 8
+APPROX_EXP_FAST, APPROX_EXP_SPLINE, APPROX_EXP_MASK = 1 << 10, 2 << 10, 3 << 10
+FN_SPLINE_ERF, FN_SPLINE_ERF_MIRROR, FN_TAYLOR_ERF, FN_AS_ERF, FN_ERF, FN_EXP, FN_FAST_EXP, FN_SPLINE_EXP = range(8)
 MODE1 = ERF_EXACT | LIST_ALL | QUANT_TRUNCATE | ALPHA_OPAQUE
 MODE4 = ERF_AS | LIST_ALL | QUANT_NEAREST | ALPHA_OPAQUE
 MODE5 = ERF_EXACT | LIST_REFERENCE | QUANT_TRUNCATE | ALPHA_OPAQUE
@@ -194,6 +198,14 @@ class Renderer:
     def frame_render(self, frame, want_image=True, want_radiance=False):
         self.tile(frame)
         return self.render(frame, want_image, want_radiance)
+
+    def approx_table(self, fn, x):
+        """y = f(x) on the device for one of the FN_* functions (the columns tests/accuracy.cpp tabulates)."""
+        xv = _f32(x).reshape(-1)
+        out = np.zeros_like(xv)
+        self._check(self._lib.vrt_cuda_approx_table(self._h, int(fn), xv.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), len(xv)),
+                    "vrt_cuda_approx_table")
+        return out
 
     def fp32_peak(self, packed=False):
         out = ctypes.c_double()

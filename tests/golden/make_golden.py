@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle_lib import Ref  # noqa: E402
+from oracle_lib import APPROX_FNS, Ref, variant_code  # noqa: E402
 
 import __graft_entry__ as ge  # noqa: E402
 
@@ -102,6 +102,58 @@ def main():
 
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_outputs.npz"), {k: v.shape for k, v in out.items()})
+    approx_golden(pkg)
+
+
+# variant combinations (erf, exp) pinned by radiance fixtures; the first two are the FOG / MINE columns of tests/img-error.cpp
+APPROX_VARIANTS = (("as", "exact"), ("as", "fast"), ("spline", "exact"), ("spline_mirror", "exact"), ("taylor", "exact"),
+                   ("exact", "spline"), ("spline", "fast"), ("taylor", "spline"))
+
+
+def approx_golden(pkg):
+    """8. the alternative approximations (src/vrt/approx.h:10-46): tables on the grids of tests/accuracy.cpp (plus every
+    spline knot and its neighbours), scalar-path radiance of the img-error scene for several <Exp, Erf> combinations, and
+    the MSE figures tests/img-error.cpp prints (SIMD tiled entry vs the scalar exact image)."""
+    out = {}
+    knots_e = np.array([-2.9 + 0.6 * i for i in range(11)], np.float32)
+    knots_x = np.array([-9, -8, -7, -6, -5, -4.5, -4, -3.5, -3, -2.5, -2, -1.75, -1.5, -1.25, -1, -0.75, -0.5, -0.25, 0], np.float32)
+    around = lambda k: np.concatenate([k, np.nextafter(k, np.float32(-100)), np.nextafter(k, np.float32(100))])
+    xe = np.concatenate([np.arange(-6.0, 6.0001, 0.1, dtype=np.float32), np.arange(-3.3, 3.3, 0.0137, dtype=np.float32), around(knots_e),
+                         np.array([-2.0, 2.0, 0.0, -0.0], np.float32)])
+    xx = np.concatenate([np.arange(-16.0, 0.0001, 0.1, dtype=np.float32), np.arange(-10.0, 0.4, 0.0171, dtype=np.float32), around(knots_x),
+                         np.array([-87.0, -88.5, -100.0, -1000.0], np.float32)])
+    out["erf_x"], out["exp_x"] = xe, xx
+    for fn, name in enumerate(APPROX_FNS):
+        out[f"table_{name}"] = Ref.approx_table(fn, xe if fn < 5 else xx)
+    out["table_fast_exp_simd"] = Ref.approx_table(6, xx, simd=True)
+
+    g16 = pkg.scenes.img_error_grid()
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    origin = np.zeros(4, np.float32)
+    w, h, counts, idx = Ref.tile_membership(np.float32(1.0 / 8.0), np.float32(1.0 / 8.0), g16, ident)
+    offs = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    pix = np.arange(11, 256 * 256, 397, dtype=np.uint64)
+    dirs = Ref.pixel_dirs((0, 0, 0), -90.0, 0.0, 1.0, 256, 256, origin, pix)
+    out["ie_pix"], out["ie_dirs"] = pix, dirs
+    for erf, exp in APPROX_VARIANTS:
+        rad = np.zeros((len(pix), 4), np.float32)
+        for k, p in enumerate(pix):
+            t = (int(p) // 256 // 16) * 16 + (int(p) % 256) // 16
+            rad[k] = Ref.radiance(g16[idx[offs[t] : offs[t + 1]]], origin, dirs[k : k + 1], variant_code(erf, exp))[0]
+        out[f"ie_rad_{erf}_{exp}"] = rad
+        print("radiance", erf, exp, float(rad.max()))
+    rgb = lambda im: np.stack([(im >> s) & 0xFF for s in (0, 8, 16)], -1).astype(np.float64) / 255.0
+    ref_img = Ref.img_error_image(g16, 1.0 / 8.0, ident, 256, 256, -1, threads=8)
+    out["ie_image_scalar"] = ref_img[::5, ::5].copy()
+    for erf, exp in APPROX_VARIANTS:
+        if erf == "exact":
+            continue  # no SIMD exact erf without SVML
+        img = Ref.img_error_image(g16, 1.0 / 8.0, ident, 256, 256, variant_code(erf, exp), threads=8)
+        out[f"ie_mse_{erf}_{exp}"] = np.array([np.mean(np.sum((rgb(ref_img) - rgb(img)) ** 2, -1))])
+        out[f"ie_image_{erf}_{exp}"] = img[::5, ::5].copy()
+        print("img-error MSE", erf, exp, float(out[f"ie_mse_{erf}_{exp}"][0]))
+    np.savez_compressed(os.path.join(HERE, "reference_approx.npz"), **out)
+    print("wrote", os.path.join(HERE, "reference_approx.npz"))
 
 
 if __name__ == "__main__":

@@ -16,6 +16,16 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 
 c_f, c_d, c_i, c_u64, vp = ctypes.c_float, ctypes.c_double, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p
 
+# approximation tables (orc_approx_table / ref_approx_table) and the variant code of the radiance entry points
+APPROX_FNS = ("spline_erf", "spline_erf_mirror", "taylor_erf", "abramowitz_stegun_erf", "erff", "expf", "fast_exp", "spline_exp")
+ERF_IDS = {"exact": 0, "as": 1, "spline": 2, "spline_mirror": 3, "taylor": 4}
+EXP_IDS = {"exact": 0, "fast": 1, "spline": 2}
+
+
+def variant_code(erf="exact", exp="exact"):
+    return ERF_IDS[erf] | (EXP_IDS[exp] << 4)
+
+
 
 def _ptr(a):
     return a.ctypes.data_as(vp)
@@ -67,6 +77,7 @@ class Oracle:
             L.orc_pack_pixel.argtypes = [vp, c_i, c_i]
             L.orc_read_obj.restype = c_u64
             L.orc_read_obj.argtypes = [ctypes.c_char_p, vp, c_u64]
+            L.orc_approx_table.argtypes = [c_i, vp, c_u64, vp]
             cls._lib = L
         return cls._lib
 
@@ -74,6 +85,14 @@ class Oracle:
     def as_erf(cls, x):
         L = cls.lib()
         return np.array([L.orc_as_erf_f32(float(v)) for v in np.asarray(x, np.float32)], np.float32)
+
+    @classmethod
+    def approx_table(cls, fn, x):
+        """APPROX_FNS[fn] evaluated at x (the functions tests/accuracy.cpp tabulates)."""
+        xv = _f32(x)
+        out = np.zeros_like(xv)
+        cls.lib().orc_approx_table(fn, _ptr(xv), len(xv), _ptr(out))
+        return out
 
     @classmethod
     def transmittance(cls, gaussians, origin, direction, s, variant=0, f64=False):
@@ -205,6 +224,10 @@ class Ref:
                 L.ref_render_tile_strip.argtypes = [vp, vp, c_u64, c_u64, c_u64, vp, vp, vp, vp, c_u64, c_i, vp]
                 L.ref_read_obj.restype = c_u64
                 L.ref_read_obj.argtypes = [ctypes.c_char_p, vp, c_u64]
+                L.ref_approx_table.restype = c_i
+                L.ref_approx_table.argtypes = [c_i, vp, c_u64, vp]
+                L.ref_img_error_image.restype = c_i
+                L.ref_img_error_image.argtypes = [vp, c_u64, c_f, vp, c_u64, c_u64, c_u64, c_i, vp]
                 cls._lib = L
                 cls._path = p
         if cls._lib is None and required:
@@ -258,6 +281,22 @@ class Ref:
         out = np.zeros_like(xv)
         cls.lib().ref_as_erf(_ptr(xv), len(xv), _ptr(out))
         return out
+
+    @classmethod
+    def approx_table(cls, fn, x, simd=False):
+        xv = _f32(x)
+        out = np.zeros_like(xv)
+        if cls.lib().ref_approx_table(fn + (16 if simd else 0), _ptr(xv), len(xv), _ptr(out)) != 0:
+            raise ValueError(fn)
+        return out
+
+    @classmethod
+    def img_error_image(cls, gaussians, tw, tiling_view, w, h, variant, threads=4):
+        """tests/img-error.cpp:27-43 for one variant code (>= 0: tiled SIMD entry, < 0: the scalar reference image)."""
+        g, v = _f32(gaussians), _f32(tiling_view)
+        img = np.zeros(w * h, np.uint32)
+        cls.lib().ref_img_error_image(_ptr(g), len(g), np.float32(tw), _ptr(v), w, h, threads, variant, _ptr(img))
+        return img.reshape(h, w)
 
     @classmethod
     def render_app(cls, mode, gaussians, w, h, tiles=16, threads=1, camera_offset=-4.0, focal=1.0, initial_rot=0.0):

@@ -82,3 +82,27 @@ def channel_diff_lsb(img_a, img_b):
         b = ((img_b >> sh) & 0xFF).astype(np.int64)
         d = max(d, int(np.abs(a - b).max()))
     return d
+
+
+# ---- alternative approximations (src/vrt/approx.h:10-46) -------------------------------------------------------------
+# (abs, rel) tolerance of one table value against the reference's scalar function: a -ffast-math host build, the strict-IEEE
+# restatement and the device (FMA contraction, MUFU.RCP / MUFU.EX2) agree only to rounding.  fast_exp turns the float
+# a x + b into the result's bit pattern, so one rounding of a x (magnitude up to 2^31, ulp 2^7) is 2^7 / 2^23 = 1.5e-5 relative.
+APPROX_TOL = {
+    "spline_erf": (2e-6, 0.0),
+    "spline_erf_mirror": (2e-6, 0.0),
+    "taylor_erf": (1e-6, 0.0),
+    "abramowitz_stegun_erf": (2e-6, 0.0),
+    "erff": (5e-7, 0.0),
+    "expf": (1e-37, 4e-6),
+    "fast_exp": (1e-37, 3.2e-5),
+    "spline_exp": (1e-6, 0.0),
+}
+
+
+def table_mismatch(name, got, want, x):
+    """Largest violation of APPROX_TOL[name] (<= 0 means within tolerance).  Inputs within one ulp of a spline knot or of
+    Taylor's +-2 cut may legitimately fall on either side of a discontinuity and are judged against both neighbours."""
+    a, r = APPROX_TOL[name]
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return float((np.abs(got - want) - (a + r * np.abs(want))).max())

@@ -171,3 +171,59 @@ def test_oracle_against_compiled_reference_live(pkg):
         o64 = Oracle.radiance(g[:120], origin_r, dirs, variant, f64=True)
         assert np.abs(r - o).max() <= 5e-5, variant
         assert np.abs(r - o64).max() <= 5e-5, variant
+
+
+# ---------------------------------------------------------------- alternative approximations (approx.h:10-46)
+@pytest.fixture(scope="module")
+def gold_approx():
+    return np.load(os.path.join(GOLDEN, "reference_approx.npz"))
+
+
+def test_approx_tables_match_reference(gold_approx):
+    """The grids of tests/accuracy.cpp (plus every spline knot and its float neighbours): restated functions vs the
+    reference's scalar functions.  Segment selection at the knots must agree exactly, values to rounding."""
+    from oracle_lib import APPROX_FNS
+    from parity_util import table_mismatch
+
+    for fn, name in enumerate(APPROX_FNS):
+        x = gold_approx["erf_x"] if fn < 5 else gold_approx["exp_x"]
+        got = Oracle.approx_table(fn, x)
+        assert table_mismatch(name, got, gold_approx[f"table_{name}"], x) <= 0, name
+    got = Oracle.approx_table(8, gold_approx["exp_x"])
+    assert table_mismatch("fast_exp", got, gold_approx["table_fast_exp_simd"], gold_approx["exp_x"]) <= 0
+
+
+def test_approx_known_values():
+    """Properties the reference's functions have by construction (approx.cpp:9-23, 45-56, 64-77, 112-127, 141-163)."""
+    t = lambda fn, x: Oracle.approx_table(fn, np.array(x, np.float32))
+    assert list(t(0, [-2.9, -5.0, 3.1, 7.0])) == [-1.0, -1.0, 1.0, 1.0]  # spline_erf saturates at the outer knots
+    assert list(t(1, [-3.0, 3.0])) == [-1.0, 1.0]
+    x = np.linspace(0.05, 2.85, 57).astype(np.float32)
+    assert np.array_equal(t(1, x), -t(1, -x))  # the mirrored spline is odd by construction (except sign(0) = +1), the plain one is not
+    assert np.abs(t(0, x) + t(0, -x)).max() > 1e-3
+    assert list(t(2, [-2.0, 2.0, 0.0])) == [-1.0, 1.0, 0.0]  # taylor_erf cut at +-2
+    assert list(t(7, [-9.0, -20.0, 0.0, 1.0])) == [0.0, 0.0, 1.0, 1.0]  # spline_exp
+    assert list(t(6, [-100.0, -1000.0])) == [0.0, 0.0]  # fast_exp below the clamp
+    xe = np.linspace(-80, 0, 200).astype(np.float32)
+    assert np.abs(t(6, xe) / np.exp(xe.astype(np.float64)) - 1).max() < 0.04  # Schraudolph: a few percent everywhere
+
+
+def test_variant_radiance_matches_reference(gold_approx, pkg):
+    """Scalar-path radiance of the img-error scene with <Exp, Erf> substituted (rt.h:32, 146): restatement vs reference."""
+    from oracle_lib import variant_code
+
+    scene = pkg.scenes.img_error_grid()
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    lists = reference_lists(scene, ident, 16)
+    pix, dirs = gold_approx["ie_pix"], gold_approx["ie_dirs"]
+    origin = np.zeros(4, np.float32)
+    sel = np.arange(0, len(pix), 5)
+    for key in [k for k in gold_approx.files if k.startswith("ie_rad_")]:
+        erf, exp = key[len("ie_rad_"):].rsplit("_", 1)
+        got = np.zeros((len(sel), 4), np.float32)
+        for i, k in enumerate(sel):
+            p = int(pix[k])
+            t = (p // 256 // 16) * 16 + (p % 256) // 16
+            got[i] = Oracle.radiance(scene[lists[t]], origin, dirs[k : k + 1], variant_code(erf, exp))[0]
+        err = float(np.abs(got - gold_approx[key][sel]).max())
+        assert err <= 2e-4, (key, err)
