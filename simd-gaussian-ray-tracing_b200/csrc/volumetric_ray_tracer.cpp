@@ -37,12 +37,15 @@ static const char *const HELP_MSG =
     "  render    -m <mode>             1-8: the reference's modes (erf variant, lists, quantisation, alpha)\n"
     "                                  9: untiled semantics + k-sigma lists, 10: tiled semantics + k-sigma lists (default)\n"
     "            --bound <k> (6)       k of modes 9/10;   --gpus <n> row bands on n GPUs\n"
+    "            --erf <fn> / --exp <fn>   swap in one of the library's other approximations (the <Exp, Erf> template arguments):\n"
+    "                                  erf: as | exact | spline | spline-mirror | taylor     exp: exact | fast | spline\n"
     "  misc      -q (always headless), -t <n> (ignored: no thread pool), --help\n";
 
 struct cmd_args_t
 {
     uint64_t w = (uint64_t)-1, h = (uint64_t)-1, grid_dim = 4, thread_count = 1, nr_frames = 1, tiles = 16, mode = 10;
     uint64_t synthetic = 0, seed = 43, gpus = 1;
+    uint32_t approx_set = 0, approx_clear = 0; // flag bits forced on / off by --erf / --exp
     char *outfile = nullptr, *infile = nullptr;
     bool use_grid = false, quiet = false;
     float rot = 360.f, initial_rot = 0.f, camera_offset = -4.f, focal_length = 1.f, bound = 6.f, sig_lo = -2.6f, sig_hi = -2.0f;
@@ -59,6 +62,7 @@ struct cmd_args_t
                                        {"help", no_argument, nullptr, 0xff},           {"gpus", required_argument, nullptr, 0x100},
                                        {"bound", required_argument, nullptr, 0x101},   {"synthetic", required_argument, nullptr, 0x102},
                                        {"seed", required_argument, nullptr, 0x103},    {"sigma-range", required_argument, nullptr, 0x104},
+                                       {"erf", required_argument, nullptr, 0x105},     {"exp", required_argument, nullptr, 0x106},
                                        {nullptr, 0, nullptr, 0}};
         int lidx;
         for (;;)
@@ -96,6 +100,29 @@ struct cmd_args_t
             case 0x102: synthetic = strtoul(optarg, nullptr, 10); break;
             case 0x103: seed = strtoul(optarg, nullptr, 10); break;
             case 0x104: std::sscanf(optarg, "%f,%f", &sig_lo, &sig_hi); break;
+            case 0x105:
+            {
+                const std::string v = optarg;
+                approx_clear |= VRT_CUDA_ERF_MASK | VRT_CUDA_APPROX_ERF_MASK;
+                approx_set &= ~(VRT_CUDA_ERF_MASK | VRT_CUDA_APPROX_ERF_MASK);
+                if (v == "as") approx_set |= VRT_CUDA_ERF_AS;
+                else if (v == "exact") approx_set |= VRT_CUDA_ERF_EXACT;
+                else if (v == "spline") approx_set |= VRT_CUDA_APPROX_ERF_SPLINE;
+                else if (v == "spline-mirror") approx_set |= VRT_CUDA_APPROX_ERF_SPLINE_MIRROR;
+                else if (v == "taylor") approx_set |= VRT_CUDA_APPROX_ERF_TAYLOR;
+                else { std::fputs(HELP_MSG, stderr); std::exit(EXIT_FAILURE); }
+                break;
+            }
+            case 0x106:
+            {
+                const std::string v = optarg;
+                approx_clear |= VRT_CUDA_APPROX_EXP_MASK;
+                approx_set &= ~VRT_CUDA_APPROX_EXP_MASK;
+                if (v == "fast") approx_set |= VRT_CUDA_APPROX_EXP_FAST;
+                else if (v == "spline") approx_set |= VRT_CUDA_APPROX_EXP_SPLINE;
+                else if (v != "exact") { std::fputs(HELP_MSG, stderr); std::exit(EXIT_FAILURE); }
+                break;
+            }
             default: std::fputs(HELP_MSG, stderr); std::exit(EXIT_FAILURE);
             }
         }
@@ -184,7 +211,7 @@ int main(int argc, char **argv)
 
     const uint32_t width = (uint32_t)cmd.w, height = (uint32_t)cmd.h;
     std::vector<uint32_t> image((size_t)width * height, 0u);
-    const uint32_t flags = mode_flags(cmd.mode);
+    const uint32_t flags = (mode_flags(cmd.mode) & ~cmd.approx_clear) | cmd.approx_set;
     const bool tiled = (flags & VRT_CUDA_LIST_MASK) == VRT_CUDA_LIST_REFERENCE || (flags & VRT_CUDA_LIST_MASK) == VRT_CUDA_LIST_REFERENCE_BOUND;
 
     float angle = cmd.initial_rot; // accumulated rotation about +y (main.cpp:252-255, 330-334)

@@ -96,3 +96,19 @@ def test_dropin_with_reference_types():
     r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "dropin_check"), "4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     print(r.stdout)
     assert r.returncode == 0 and "dropin_check: PASSED" in r.stdout, r.stdout
+
+
+def test_app_approximation_flags(tmp_path):
+    """--erf / --exp (extension flags): the <Exp, Erf> substitution of tests/img-error.cpp from the command line."""
+    run_app(["-q", "-g", "4", "-m", "8", "-o", "base.png"], str(tmp_path))
+    base = read_png(str(tmp_path / "base.png"))
+    run_app(["-q", "-g", "4", "-m", "8", "--erf", "as", "--exp", "exact", "-o", "same.png"], str(tmp_path))
+    assert np.array_equal(read_png(str(tmp_path / "same.png")), base)
+    run_app(["-q", "-g", "4", "-m", "8", "--erf", "taylor", "--exp", "fast", "-o", "tf.png"], str(tmp_path))
+    tf = read_png(str(tmp_path / "tf.png"))
+    d = channel_diff_lsb(tf, base)
+    assert 0 < d <= 12, d  # a visibly different approximation of the same picture (fast_exp alone is off by up to 3 %)
+    run_app(["-q", "-g", "4", "-m", "5", "--erf", "spline-mirror", "-o", "sm.png"], str(tmp_path))
+    assert channel_diff_lsb(read_png(str(tmp_path / "sm.png")), base & 0x00FFFFFF | 0xFF000000) <= 40
+    r = subprocess.run([APP, "-q", "--erf", "bogus"], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert r.returncode != 0
