@@ -59,8 +59,13 @@ extern "C" {
  * min(1, sum albedo.w * inner) * 255 (rt.h:373, 377). */
 #define VRT_CUDA_ALPHA_OPAQUE (0u << 5)
 #define VRT_CUDA_ALPHA_FROM_W (1u << 5)
-/* Keep every list entry's terms even when its weight underflows to exactly 0 for a whole warp
- * (disables the warp-uniform skip; results are bit-identical either way, only the work differs). */
+/* Evaluate the lists literally.  By default an entry whose weight exp(-d^2 / 2 sigma^2) is exactly 0 in fp32 for every ray
+ * of an 8x4-pixel cell (farther than ~13.2 sigma from all of them) is dropped from that cell: in the literal list modes
+ * (REFERENCE, ALL, caller-supplied tiles_t) vrt_cuda_tile / vrt_cuda_set_tile_lists intersect the lists with "visible from
+ * the cell" once per frame, and K2 skips warp-uniformly what is left.  Such entries add exactly 0 to every sum, so the image
+ * is the literal one up to the order of the fp32 additions (differences ~1e-7); vrt_cuda_stats.terms_listed,
+ * vrt_cuda_get_lists and the membership they report stay literal.  NO_SKIP (given to the tile call AND the render call)
+ * keeps every entry and evaluates every listed term: terms_executed == terms_listed. */
 #define VRT_CUDA_NO_SKIP (1u << 6)
 /* Depth-window mode (bounded per-cell lists only): K1 sorts every cell's list by depth along the cell's centre ray and K2
  * resolves an occluder that lies >= t_sat standard widths in front of (behind) every sample of the current emitter block,

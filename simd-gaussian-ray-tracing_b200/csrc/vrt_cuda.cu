@@ -45,6 +45,10 @@ constexpr int SLICE_MAX = 64;      // emitters per item of a split cell: 64 on b
 constexpr int SLICE_MIN = 8;       //   items to fill the machine (always a multiple of every emitter block size Q)
 constexpr int ITEM_CELL_BITS = 22; // work item = cell id | slice << 22  (4M cells, 1024 slices)
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+// Literal list modes: a Gaussian farther than this many sigma from every ray of a cell has weight exp(-d^2 / 2 sigma^2) <
+// 2^-126, which MUFU.EX2 (.ftz) returns as exactly 0 -- it contributes exactly 0 to every sum of the cell (13.22 sigma is the
+// exact limit; the margin covers fp32 rounding of d^2 and fast_exp's clamp at 13.27 sigma).
+constexpr float VISIBLE_SIGMAS = 13.4f;
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float SQRT_PI_2 = 1.2533141373155003f; // sqrt(pi/2) = 1/0.7978845608 (INV_SQRT_2_PI of src/vrt/rt.h:19)
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
             uint32_t gi = 0;
             if (e < end)
             {
-                gi = L.is_root ? e : parent_idx[e];
+                gi = (L.is_root || parent_idx == nullptr) ? e : parent_idx[e]; // no index array: the parent list is a contiguous range
                 const float4 a = cullrec[2 * gi]; // (oc.xyz, sigma)
                 const float4 cr = G.use_ref ? cullrec[2 * gi + 1] : make_float4(0.f, 0.f, 0.f, 1.f);
                 pass = cull_test(rc, a, a.w, cr);
@@ -1752,6 +1756,7 @@ struct vrt_cuda_ctx
     DevBuf out_image, out_rad;
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
     DevBuf tile_off;
+    DevBuf lit_offsets, lit_idx; // literal lists (tile_gaussians membership) kept for vrt_cuda_get_lists while K2 uses the visible lists
 
     // state of the last tile()
     bool have_lists = false;
@@ -1765,6 +1770,13 @@ struct vrt_cuda_ctx
     uint32_t n_queue = 0;
     int cy_begin = 0, cy_end = 0;
     uint32_t launches = 0, render_launches = 0; // kernels of the last tile() / render()
+    // literal list modes with culling: the lists K2 walks are "literal membership AND visible from the cell" (see
+    // visible_pass); what the literal lists were is kept here
+    bool literal = false;
+    int lit_kind = 0;
+    uint32_t lit_n_lists = 0;
+    uint64_t lit_n_entries = 0;
+    TileStats lit_stats{};
     float ms_tile = 0.f;
     // tuning
     int tune_q = 0; // 0 = automatic: 8 emitters per register block, 4 when the lists are short
@@ -2151,7 +2163,7 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
-                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off};
+                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off, &ctx->lit_offsets, &ctx->lit_idx};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (int i = 0; i < 4; ++i)
@@ -2308,7 +2320,8 @@ int vrt_cuda_mix_peak(vrt_cuda_ctx *ctx, int nf, int nm, int nl, double *steps_p
     return 0;
 }
 
-int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
+// K0 + K1 for one frame: records, lists of the frame's list mode, depth sort, work queue
+static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
     CU(cudaSetDevice(ctx->device));
@@ -2317,6 +2330,7 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     if (int rc = make_geom(ctx, frame, -1, G, cxs, cys)) return rc;
     ctx->have_lists = false;
     ctx->lists_from_host = false;
+    ctx->literal = false;
     ctx->geom = G;
     ctx->launches = 0;
     const uint64_t N = ctx->n_gauss;
@@ -2438,6 +2452,43 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     return 0;
 }
 
+// Literal list modes (the reference's tile membership, the ALL list, caller-supplied tiles_t) name far more Gaussians per
+// pixel than the pixel can see: an entry farther than VISIBLE_SIGMAS sigma from every ray of a cell has a weight of exactly
+// 0 there and adds exactly 0 to every sum.  Instead of discovering that per (occluder, emitter block) inside the n^2 loop,
+// K1 intersects the literal lists with "visible from the cell" once per frame and K2 walks those per-cell lists (depth-
+// sorted, split, queued like the bounded modes).  The literal lists stay available to vrt_cuda_get_lists and the literal
+// counts to vrt_cuda_stats; the image is the literal one up to the order of the fp32 sums.  VRT_CUDA_NO_SKIP turns this off.
+static int keep_literal(vrt_cuda_ctx *ctx)
+{
+    CU(cudaMemcpyAsync(&ctx->lit_stats, ctx->stats.p, sizeof(TileStats), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->coffsets, ctx->lit_offsets);
+    std::swap(ctx->cidx, ctx->lit_idx);
+    ctx->lit_kind = ctx->geom.list_kind;
+    ctx->lit_n_lists = ctx->n_lists;
+    ctx->lit_n_entries = ctx->n_entries;
+    return 0;
+}
+
+int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
+{
+    if (int rc = tile_build(ctx, frame)) return rc;
+    const uint32_t lm = frame->flags & VRT_CUDA_LIST_MASK;
+    if ((lm != VRT_CUDA_LIST_REFERENCE && lm != VRT_CUDA_LIST_ALL) || (frame->flags & VRT_CUDA_NO_SKIP) || ctx->n_gauss == 0) return 0;
+    ctx->have_lists = false;
+    if (int rc = keep_literal(ctx)) return rc;
+    const float ms_literal = ctx->ms_tile;
+    const uint32_t launches_literal = ctx->launches;
+    vrt_cuda_frame visible = *frame;
+    visible.flags = (frame->flags & ~VRT_CUDA_LIST_MASK) | (lm == VRT_CUDA_LIST_REFERENCE ? VRT_CUDA_LIST_REFERENCE_BOUND : VRT_CUDA_LIST_BOUND);
+    visible.bound_sigmas = VISIBLE_SIGMAS;
+    if (int rc = tile_build(ctx, &visible)) return rc;
+    ctx->ms_tile += ms_literal;
+    ctx->launches += launches_literal;
+    ctx->literal = true;
+    return 0;
+}
+
 int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, const float *aos_concat, const uint64_t *offsets, uint64_t n_tiles)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
@@ -2457,25 +2508,72 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
         off32[t] = (uint32_t)offsets[t];
     }
     ctx->have_lists = false;
+    ctx->literal = false;
     ctx->geom = G;
     ctx->launches = 0;
     if (int rc = upload_geom(ctx, G, cxs, cys)) return rc;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (int rc = reserve(ctx, ctx->tile_aos, std::max<uint64_t>(total, 1) * 40)) return rc;
     if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(total, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->cullrec, 2 * sizeof(float4) * std::max<uint64_t>(total, 1))) return rc;
     if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (n_tiles + 1))) return rc;
     if (total) CU(cudaMemcpyAsync(ctx->tile_aos.p, aos_concat, total * 40, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->coffsets.p, off32.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (total)
     {
-        k0_prepare<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->tile_aos.p, total, (Rec *)ctx->rec.p, nullptr);
+        k0_prepare<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->tile_aos.p, total, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
     ctx->n_lists = (uint32_t)n_tiles;
     ctx->n_entries = total;
     ctx->lists_from_host = true;
+    ctx->lists_sorted = false;
     if (int rc = build_queue(ctx)) return rc;
+    if (total && !(frame->flags & VRT_CUDA_NO_SKIP))
+    {
+        // visible lists (see vrt_cuda_tile): one cull level, every 8x4 cell scans the record range of its own tile
+        CU(cudaStreamSynchronize(ctx->stream)); // off32 (stack) is consumed before the offsets buffer changes hands
+        if (int rc = keep_literal(ctx)) return rc;
+        FrameGeom V = G;
+        V.list_kind = 0;
+        V.use_ref = 0;
+        V.use_bound = 1;
+        V.bound_k = VISIBLE_SIGMAS;
+        ctx->geom = V;
+        if (int rc = upload_geom(ctx, V, cxs, cys)) return rc;
+        CullLevel L{};
+        L.gx = L.gy = 1;
+        L.ngx = V.ncx; L.ngy = V.ncy;
+        L.pgx = V.cptx; L.pgy = V.cpty; L.pngx = V.tiles_x;
+        L.is_root = 0; L.n_seg = 1;
+        const uint64_t cells = (uint64_t)V.ncx * V.ncy;
+        if (cells > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "image too large");
+        if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * cells)) return rc;
+        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (cells + 1))) return rc;
+        const unsigned grid = (unsigned)((cells * 32 + 255) / 256);
+        k1_cull<false><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr,
+                                                     (uint32_t *)ctx->ccounts.p, nullptr, nullptr, (uint32_t)cells);
+        if (int rc = scan_u32(ctx, (const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, (uint32_t)cells)) return rc;
+        uint32_t kept = 0;
+        CU(cudaMemcpyAsync(&kept, (const uint32_t *)ctx->coffsets.p + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(kept, 1))) return rc;
+        k1_cull<true><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr, nullptr,
+                                                    (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, (uint32_t)cells);
+        ctx->launches += 2;
+        ctx->n_lists = (uint32_t)cells;
+        ctx->n_entries = kept;
+        if (kept)
+        {
+            k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
+            ctx->launches++;
+            ctx->lists_sorted = true;
+        }
+        CU(cudaGetLastError());
+        if (int rc = build_queue(ctx)) return rc;
+        ctx->literal = true;
+    }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream)); // off32 lives on this stack frame
     CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
@@ -2488,26 +2586,32 @@ int vrt_cuda_get_lists(vrt_cuda_ctx *ctx, uint32_t *counts_out, uint64_t counts_
     if (!ctx) return VRT_CUDA_E_INVALID;
     if (!ctx->have_lists) return fail(ctx, VRT_CUDA_E_STATE, "no lists: call vrt_cuda_tile first");
     CU(cudaSetDevice(ctx->device));
-    if (n_cells_out) *n_cells_out = ctx->n_lists;
-    if (n_entries_out) *n_entries_out = ctx->n_entries;
+    // literal modes report the literal lists (the membership of tile_gaussians), not the visible subsets K2 walks
+    const uint32_t n_lists = ctx->literal ? ctx->lit_n_lists : ctx->n_lists;
+    const uint64_t n_entries = ctx->literal ? ctx->lit_n_entries : ctx->n_entries;
+    const int kind = ctx->literal ? ctx->lit_kind : ctx->geom.list_kind;
+    const DevBuf &offsets = ctx->literal ? ctx->lit_offsets : ctx->coffsets;
+    const DevBuf &indices = ctx->literal ? ctx->lit_idx : ctx->cidx;
+    if (n_cells_out) *n_cells_out = n_lists;
+    if (n_entries_out) *n_entries_out = n_entries;
     if (counts_out)
     {
-        if (counts_cap < ctx->n_lists) return fail(ctx, VRT_CUDA_E_INVALID, "counts_cap too small");
-        std::vector<uint32_t> off(ctx->n_lists + 1);
-        CU(cudaMemcpyAsync(off.data(), ctx->coffsets.p, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        if (counts_cap < n_lists) return fail(ctx, VRT_CUDA_E_INVALID, "counts_cap too small");
+        std::vector<uint32_t> off(n_lists + 1);
+        CU(cudaMemcpyAsync(off.data(), offsets.p, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t i = 0; i < ctx->n_lists; ++i) counts_out[i] = off[i + 1] - off[i];
+        for (uint32_t i = 0; i < n_lists; ++i) counts_out[i] = off[i + 1] - off[i];
     }
     if (idx_out)
     {
-        if (idx_cap < ctx->n_entries) return fail(ctx, VRT_CUDA_E_INVALID, "idx_cap too small");
-        if (ctx->geom.list_kind == 2 || ctx->lists_from_host)
+        if (idx_cap < n_entries) return fail(ctx, VRT_CUDA_E_INVALID, "idx_cap too small");
+        if (kind == 2 || ctx->lists_from_host)
         {
-            for (uint64_t i = 0; i < ctx->n_entries; ++i) idx_out[i] = (uint32_t)i;
+            for (uint64_t i = 0; i < n_entries; ++i) idx_out[i] = (uint32_t)i;
         }
-        else if (ctx->n_entries)
+        else if (n_entries)
         {
-            CU(cudaMemcpyAsync(idx_out, ctx->cidx.p, sizeof(uint32_t) * ctx->n_entries, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(idx_out, indices.p, sizeof(uint32_t) * n_entries, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
     }
@@ -2554,7 +2658,9 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     RenderArgs a{};
     a.rec = (const Rec *)ctx->rec.p;
     a.list_off = (const uint32_t *)ctx->coffsets.p;
-    a.list_idx = (G.list_kind == 2 || ctx->lists_from_host) ? nullptr : (const uint32_t *)ctx->cidx.p;
+    a.list_idx = (G.list_kind == 2 || (ctx->lists_from_host && !ctx->literal)) ? nullptr : (const uint32_t *)ctx->cidx.p;
+    if (ctx->literal && (frame->flags & VRT_CUDA_NO_SKIP))
+        return fail(ctx, VRT_CUDA_E_STATE, "these lists were built with culling: pass VRT_CUDA_NO_SKIP to vrt_cuda_tile / vrt_cuda_set_tile_lists as well");
     a.queue = (const uint32_t *)ctx->queue.p;
     a.n_queue = ctx->n_queue;
     a.counter = (uint32_t *)ctx->counter.p;
@@ -2568,7 +2674,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         if (int rc = reserve(ctx, ctx->partial, (size_t)ctx->n_split * 32 * sizeof(float4))) return rc;
     a.partial = (float4 *)ctx->partial.p;
     const bool bounded = G.use_bound != 0;
-    a.skip_thresh = (frame->flags & VRT_CUDA_NO_SKIP) ? -1.f : (bounded ? std::exp2(-0.5f * G.bound_k * G.bound_k * LOG2E) : 0.f);
+    a.skip_thresh = (frame->flags & VRT_CUDA_NO_SKIP) ? -1.f : ((bounded && !ctx->literal) ? std::exp2(-0.5f * G.bound_k * G.bound_k * LOG2E) : 0.f);
     a.quant_nearest = (frame->flags & VRT_CUDA_QUANT_NEAREST) ? 1u : 0u;
     a.alpha_from_w = (frame->flags & VRT_CUDA_ALPHA_FROM_W) ? 1u : 0u;
     CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));
@@ -2599,11 +2705,11 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         CU(cudaStreamSynchronize(ctx->stream));
         std::memset(stats, 0, sizeof(*stats));
         stats->n_gaussians = ctx->n_gauss;
-        stats->n_cells = ctx->n_lists;
-        stats->list_entries = ts.entries;
-        stats->max_list = (uint32_t)ts.max_list;
+        stats->n_cells = ctx->literal ? ctx->lit_n_lists : ctx->n_lists;
+        stats->list_entries = ctx->literal ? ctx->lit_stats.entries : ts.entries;
+        stats->max_list = (uint32_t)(ctx->literal ? ctx->lit_stats.max_list : ts.max_list);
         stats->n_launches = ctx->launches + ctx->render_launches;
-        stats->terms_listed = ts.terms_listed;
+        stats->terms_listed = ctx->literal ? ctx->lit_stats.terms_listed : ts.terms_listed;
         stats->terms_executed = (double)ts.terms_exec;
         stats->terms_saturated = (double)ts.terms_sat;
         stats->ms_tile = ctx->ms_tile;
