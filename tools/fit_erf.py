@@ -1,4 +1,4 @@
-"""Fit the FMA-pipe polynomial of the exact-erf variant (csrc/vrt_cuda.cu: erf_exact).
+"""Fit the FMA-pipe polynomial of the exact-erf variant (csrc/vrt_common.cuh: erf_exact).
 
     erf(x) ~= 1 - 2^(-x * P(x)),  x in [0, XMAX],  P of degree DEG   (x is clamped to XMAX on the device)
 
