@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define VRT_CUDA_ABI_VERSION 3
+#define VRT_CUDA_ABI_VERSION 4
 
 /* Error codes */
 #define VRT_CUDA_OK 0
@@ -133,7 +133,7 @@ typedef struct vrt_cuda_stats
     float ms_tile;            /* device time of the cull/tile kernels (CUDA events)                       */
     float ms_render;          /* device time of the render kernel(s)                                      */
     float ms_total;           /* first kernel to last kernel / copy of the call                           */
-    float reserved;
+    uint32_t slice;           /* emitters per work item of split cells used by this frame (see vrt_cuda_set_slice)  */
     double terms_saturated;   /* depth-window mode: terms resolved by the saturation shortcut (not in terms_executed) */
 } vrt_cuda_stats;
 
@@ -197,6 +197,15 @@ int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, u
 /* Kernel tuning knob for benchmarks (not part of the reference's surface): emitters per register block
  * Q in {2,4,6,8} and packed f32x2 arithmetic on (1) / off (0).  Defaults are the tuned values. */
 int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
+
+/* Work items of heavy cells.  A cell whose list is longer than 3 x slice entries is rendered as ceil(n / slice) independent
+ * items (emitter ranges) whose partial radiances are summed in slice order; the fp32 result depends on the grouping, so two
+ * renders are bit-identical only if they use the same slice.  slice = 0 (default) picks it per frame from the listed work;
+ * a multi-GPU caller that wants its gathered bands to equal a single-GPU frame bit for bit asks for the automatic choice
+ * of the FULL frame at its share of the work (vrt_cuda_auto_slice after a full-frame vrt_cuda_tile, share = 1 / ranks) and
+ * sets it on every rank. */
+int vrt_cuda_set_slice(vrt_cuda_ctx *ctx, int slice);
+int vrt_cuda_auto_slice(vrt_cuda_ctx *ctx, double share, int *slice_out);
 
 /* Roofline probe: FP32 FMA throughput of the context's GPU in TFLOP/s (FMA = 2 flops), measured with
  * independent FFMA chains (packed_f32x2 = 0) or FFMA2 chains (1).  bench.py reports it beside the nominal peak. */

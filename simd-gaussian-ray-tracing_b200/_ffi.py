@@ -45,12 +45,12 @@ class Stats(ctypes.Structure):
         ("ms_tile", c_f),
         ("ms_render", c_f),
         ("ms_total", c_f),
-        ("reserved", c_f),
+        ("slice", c_u32),
         ("terms_saturated", c_d),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 # every symbol include/vrt_cuda.h declares: name -> (restype, argtypes)
@@ -73,6 +73,8 @@ CUDA_SYMBOLS = {
     "vrt_cuda_term_peak": (c_i, [vp, c_i, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_mix_peak": (c_i, [vp, c_i, c_i, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_approx_table": (c_i, [vp, c_i, vp, vp, c_u64]),
+    "vrt_cuda_set_slice": (c_i, [vp, c_i]),
+    "vrt_cuda_auto_slice": (c_i, [vp, c_d, ctypes.POINTER(c_i)]),
     "vrt_cuda_sync": (c_i, [vp]),
     "vrt_cuda_stream": (c_u64, [vp]),
     "vrt_cuda_device": (c_i, [vp]),

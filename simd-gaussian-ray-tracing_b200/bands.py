@@ -44,6 +44,24 @@ def balanced_bands(renderer, n_parts, height, align):
     return split_rows(rows, row_px, n_parts, height, align)
 
 
+def rebalance(row_cost, row_px, bounds, measured_ms, height, align):
+    """Feedback step of the band balance: the n^2 cost model is only proportional to time up to a factor that varies over the
+    image (list lengths change the share of per-occluder setup, K1 is not in the model), so after a frame every rank reports
+    its device time and each band's rows are re-weighted by that band's measured time per unit of modelled cost; the bands are
+    then split again.  An orbiting camera changes the picture slowly, so the previous frame is a good predictor
+    (one or two steps bring the slowest rank within a few percent of the mean).  Returns the new n_parts+1 pixel rows."""
+    row_cost = np.asarray(row_cost, np.float64)
+    weighted = row_cost.copy()
+    floor = max(row_cost.sum(), 1.0) * 1e-6  # empty rows still cost their band something
+    for r, ms in enumerate(measured_ms):
+        a, b = bounds[r] // row_px, (bounds[r + 1] + row_px - 1) // row_px
+        if b <= a:
+            continue
+        modelled = row_cost[a:b].sum() + floor * (b - a)
+        weighted[a:b] = (row_cost[a:b] + floor) * (float(ms) / modelled)
+    return split_rows(weighted, row_px, len(measured_ms), height, align)
+
+
 def gather_bands(image, bounds, rank, world, dist):
     """Rank r owns rows [bounds[r], bounds[r+1]) of `image` (a [H, W] tensor on every rank); after the call rank 0
     holds every band.  One grouped batch of point-to-point transfers (ncclSend/ncclRecv under NCCL)."""

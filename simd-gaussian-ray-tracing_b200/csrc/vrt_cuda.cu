@@ -94,6 +94,9 @@ struct vrt_cuda_ctx
     TileStats lit_stats{};
     float ms_tile = 0.f;
     // tuning
+    double q_terms_listed = 0.0; // listed terms / longest list of the lists the queue was last built for
+    uint32_t q_max_list = 0;
+    int tune_slice = 0; // 0 = automatic (auto_slice)
     int tune_q = 0; // 0 = automatic: 8 emitters per register block, 4 when the lists are short
     int tune_pack = 1;
 };
@@ -247,6 +250,17 @@ int scan_u32(vrt_cuda_ctx *ctx, const uint32_t *counts, uint32_t *offsets, uint3
 }
 
 // cost ordering of the band's cells + listed-term statistics
+// Slice size of split cells: as large as possible (every item repeats pass A), but no item may exceed a quarter of the
+// average work per resident warp, or the longest lists would decide the frame time on small frames.  `share` scales the
+// listed work (a rank that renders 1/N of the frame the lists were built for).
+int auto_slice(const vrt_cuda_ctx *ctx, double share)
+{
+    const double per_warp = ctx->q_terms_listed * share / ((double)ctx->sm_count * 12.0);
+    int slice = SLICE_MAX;
+    while (slice > SLICE_MIN && 160.0 * slice * (double)ctx->q_max_list > per_warp / 4.0) slice /= 2;
+    return slice;
+}
+
 int build_queue(vrt_cuda_ctx *ctx)
 {
     const FrameGeom &G = ctx->geom;
@@ -282,10 +296,9 @@ int build_queue(vrt_cuda_ctx *ctx)
     {
         // Slice size of split cells: as large as possible (every item repeats pass A), but no item may exceed a quarter of
         // the average work per resident warp, or the longest lists would decide the frame time on small frames.
-        const double per_warp = ts.terms_listed / ((double)ctx->sm_count * 12.0);
-        int slice = SLICE_MAX;
-        while (slice > SLICE_MIN && 160.0 * slice * (double)ts.max_list > per_warp / 4.0) slice /= 2;
-        ctx->geom.slice = slice;
+        ctx->q_terms_listed = ts.terms_listed;
+        ctx->q_max_list = (uint32_t)ts.max_list;
+        ctx->geom.slice = ctx->tune_slice ? ctx->tune_slice : auto_slice(ctx, 1.0);
         CU(cudaMemcpyToSymbolAsync(c_geom, &ctx->geom, sizeof(FrameGeom), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
     k1_hist<true><<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, nullptr, cyb, cye);
@@ -331,7 +344,9 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
 {
     // Q = 8 (236 registers, 8 warps/SM) measured fastest on B200: instruction-level parallelism across 40 independent
     // sample chains per thread beats occupancy (tools/tune_k2.py); short lists waste less padding with Q = 4
-    const int q = ctx->tune_q ? ctx->tune_q : ((ctx->n_lists && ctx->n_entries / ctx->n_lists >= 24) ? 8 : 4);
+    // mean list length over the lists that are actually rendered: a row band leaves the per-cell lists outside it empty
+    const uint64_t lists_in_band = ctx->geom.list_kind == 0 ? (uint64_t)std::max(0, ctx->cy_end - ctx->cy_begin) * ctx->geom.ncx : ctx->n_lists;
+    const int q = ctx->tune_q ? ctx->tune_q : ((lists_in_band && ctx->n_entries / lists_in_band >= 24) ? 8 : 4);
     const bool p = ctx->tune_pack != 0;
     if (a.window)
     {
@@ -509,6 +524,23 @@ int vrt_cuda_approx_table(vrt_cuda_ctx *ctx, int fn, const float *x, float *y, u
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(y, dy, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vrt_cuda_set_slice(vrt_cuda_ctx *ctx, int slice)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (slice != 0 && slice != 8 && slice != 16 && slice != 32 && slice != 64) return fail(ctx, VRT_CUDA_E_INVALID, "slice must be 0 (automatic), 8, 16, 32 or 64");
+    ctx->tune_slice = slice;
+    return 0;
+}
+
+int vrt_cuda_auto_slice(vrt_cuda_ctx *ctx, double share, int *slice_out)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!ctx->have_lists) return fail(ctx, VRT_CUDA_E_STATE, "no lists: call vrt_cuda_tile first");
+    if (!slice_out || !(share > 0.0 && share <= 1.0)) return fail(ctx, VRT_CUDA_E_INVALID, "share must be in (0, 1]");
+    *slice_out = auto_slice(ctx, share);
     return 0;
 }
 
@@ -1030,6 +1062,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         stats->ms_tile = ctx->ms_tile;
         CU(cudaEventElapsedTime(&stats->ms_render, ctx->ev[2], ctx->ev[3]));
         stats->ms_total = stats->ms_tile + stats->ms_render;
+        stats->slice = (uint32_t)G.slice;
     }
     return 0;
 }

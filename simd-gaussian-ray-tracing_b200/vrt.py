@@ -207,6 +207,14 @@ class Renderer:
                     "vrt_cuda_approx_table")
         return out
 
+    def set_slice(self, slice_):
+        self._check(self._lib.vrt_cuda_set_slice(self._h, int(slice_)), "vrt_cuda_set_slice")
+
+    def auto_slice(self, share=1.0):
+        out = ctypes.c_int()
+        self._check(self._lib.vrt_cuda_auto_slice(self._h, float(share), ctypes.byref(out)), "vrt_cuda_auto_slice")
+        return int(out.value)
+
     def fp32_peak(self, packed=False):
         out = ctypes.c_double()
         self._check(self._lib.vrt_cuda_fp32_peak(self._h, int(packed), ctypes.byref(out)), "vrt_cuda_fp32_peak")

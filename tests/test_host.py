@@ -25,7 +25,7 @@ def test_cuda_library_exports_every_declared_symbol(pkg):
     for sym in declared:
         assert hasattr(lib, sym), f"libvrt_cuda.so does not export {sym}"
     assert sorted(pkg._ffi.CUDA_SYMBOLS) == declared
-    assert lib.vrt_cuda_abi_version() == 3
+    assert lib.vrt_cuda_abi_version() == 4
 
 
 def test_host_library_exports_every_declared_symbol(pkg):
