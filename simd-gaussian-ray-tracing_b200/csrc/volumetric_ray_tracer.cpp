@@ -254,6 +254,11 @@ int main(int argc, char **argv)
             for (double &c : gcost) c += (sum > 0 ? sum : 1.0) * 1e-6;
             std::vector<uint32_t> bounds(n_gpus + 1);
             vrt_host_row_bands(gcost.data(), (uint32_t)gcost.size(), (uint32_t)n_gpus, bounds.data());
+            // one slice size on every GPU (the full frame's choice at a 1/n share): the bands then compose to exactly the
+            // image a single GPU renders
+            int slice = 0;
+            if (vrt_cuda_auto_slice(ctx[0], 1.0 / n_gpus, &slice) != VRT_CUDA_OK) DIE(ctx[0], "vrt_cuda_auto_slice");
+            for (int d = 0; d < n_gpus; ++d) vrt_cuda_set_slice(ctx[d], slice);
             const double t1 = now_ms();
             std::vector<std::thread> workers;
             std::vector<vrt_cuda_stats> sts(n_gpus);
