@@ -290,6 +290,42 @@ def test_row_bands_compose(pkg, renderer):
     assert terms == st["terms_listed"]
 
 
+def test_thin_bands_of_a_dense_frame_compose_bit_exactly(pkg, renderer):
+    """The multi-GPU contract: bands rendered by different contexts compose to exactly the single-GPU frame.  Needs (i) the
+    same kernel variant for a band as for the frame (the mean list length is taken over the band's own cells -- a thin band
+    of a dense frame once fell back to the short-list kernel), and (ii) one slice size for split cells on every rank
+    (vrt_cuda_auto_slice of the full frame at a 1/N share, vrt_cuda_set_slice)."""
+    V = pkg.vrt
+    W, parts = 512, 8
+    scene = pkg.scenes.synthetic(30000, 5, -1.9, -1.3)
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    flags = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+    f = renderer.frame(cam.view_matrix, origin, W, W, flags, (32, 32))
+    renderer.tile(f)
+    slice_ = renderer.auto_slice(1.0 / parts)
+    assert slice_ in (8, 16, 32, 64) and renderer.auto_slice(1.0) >= slice_
+    try:
+        renderer.set_slice(slice_)
+        img, rad, st = renderer.frame_render(f, True, True)
+        assert st["slice"] == slice_ and st["list_entries"] / (W * W / 32) >= 24  # long lists: the Q = 8 kernel
+        img2, rad2 = np.zeros_like(img), np.zeros_like(rad)
+        for k in range(parts):
+            fb = renderer.frame(cam.view_matrix, origin, W, W, flags, (32, 32), rows=(k * W // parts, (k + 1) * W // parts))
+            renderer.tile(fb)
+            _, _, s = renderer.render(fb, True, True, image=img2, radiance=rad2)
+            assert s["slice"] == slice_
+        assert np.array_equal(img, img2) and np.array_equal(rad, rad2)
+        # another slice size is another grouping of the same fp32 sums
+        renderer.set_slice(8 if slice_ != 8 else 64)
+        _, rad3, _ = renderer.frame_render(f, False, True)
+        assert float(np.abs(rad3 - rad).max()) <= 2e-5
+        with pytest.raises(V.VrtCudaError):
+            renderer.set_slice(24)
+    finally:
+        renderer.set_slice(0)
+
+
 def test_bound_mode_matches_all(pkg, renderer):
     """Small-sigma scene.  (1) the bounded lists change nothing visible; (2) parity against the arbiter.
 
