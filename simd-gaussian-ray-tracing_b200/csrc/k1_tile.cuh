@@ -202,9 +202,13 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
     }
     else
     {
+        // the parent's list, cut into n_seg pieces of whole 32-entry steps (coarse levels have few groups and long parent
+        // lists: one warp per group would leave most SMs idle behind a serial scan)
         const uint32_t parent = (uint32_t)((cy0 / L.pgy) * L.pngx + (cx0 / L.pgx));
-        begin = parent_off[parent];
-        end = parent_off[parent + 1];
+        const uint32_t pb = parent_off[parent], pe = parent_off[parent + 1];
+        const uint32_t per = (((pe - pb) + L.n_seg - 1) / L.n_seg + 31u) & ~31u;
+        begin = min(pe, pb + seg * per);
+        end = min(pe, begin + per);
     }
     // groups outside the rendered row band get empty lists
     const bool in_band = y1 > G.row_begin && y0 < G.row_end;

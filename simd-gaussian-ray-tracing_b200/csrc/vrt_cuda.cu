@@ -732,7 +732,15 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
             L.gx = gxs[i]; L.gy = gys[i];
             L.ngx = (G.ncx + L.gx - 1) / L.gx; L.ngy = (G.ncy + L.gy - 1) / L.gy;
             L.is_root = levels.empty() ? 1 : 0;
-            L.n_seg = L.is_root ? (int)std::max<uint64_t>(1, (N + ROOT_SEG - 1) / ROOT_SEG) : 1;
+            if (L.is_root) L.n_seg = (int)std::max<uint64_t>(1, (N + ROOT_SEG - 1) / ROOT_SEG);
+            else
+            {
+                // enough warps to fill the GPU: groups that intersect the row band x segments >= 16 warps per SM
+                const int px_h = L.gy * CELL_H; // group height in pixels (uniform grids; an estimate otherwise)
+                const int rows_hit = std::max(1, std::min(L.ngy, (G.row_end + px_h - 1) / px_h) - std::min(L.ngy - 1, G.row_begin / px_h));
+                const int64_t active = (int64_t)L.ngx * rows_hit;
+                L.n_seg = (int)std::min<int64_t>(32, std::max<int64_t>(1, ((int64_t)ctx->sm_count * 16 + active - 1) / active));
+            }
             if (!levels.empty()) { L.pgx = levels.back().gx; L.pgy = levels.back().gy; L.pngx = levels.back().ngx; }
             levels.push_back(L);
         }
