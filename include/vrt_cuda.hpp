@@ -119,6 +119,30 @@ namespace cuda
     }
 } // namespace cuda
 
+// ---- the <Exp, Erf> template arguments ---------------------------------------------------------------------------------
+// The reference selects its approximations at compile time (rt.h:32, 315, 344; tests/img-error.cpp:40-43).  Here they are
+// frame flags: cuda::approx_flags(mode, exp, erf) rewrites a VRT_CUDA_MODE* set so that, for example,
+//     simd_render_image<approx::simd_fast_exp, approx::simd_abramowitz_stegun_erf>(w, h, img, cam, origin, tiles, running, tc)
+// becomes
+//     cuda_simd_render_image(w, h, img, cam, origin, tiles, running, tc, cuda::approx_flags(VRT_CUDA_MODE8, cuda::exp_fn::fast, cuda::erf_fn::as)).
+namespace cuda
+{
+    enum class exp_fn { exact, fast, spline };                        // expf / vcl_exp, fast_exp, spline_exp        (approx.h:35-46)
+    enum class erf_fn { as, exact, spline, spline_mirror, taylor };   // A&S, erff, spline_erf, _mirror, taylor_erf  (approx.h:10-33)
+
+    constexpr uint32_t approx_flags(uint32_t mode_flags, exp_fn e, erf_fn f)
+    {
+        uint32_t flags = mode_flags & ~(VRT_CUDA_ERF_MASK | VRT_CUDA_APPROX_ERF_MASK | VRT_CUDA_APPROX_EXP_MASK);
+        flags |= e == exp_fn::fast ? VRT_CUDA_APPROX_EXP_FAST : (e == exp_fn::spline ? VRT_CUDA_APPROX_EXP_SPLINE : 0u);
+        flags |= f == erf_fn::exact    ? VRT_CUDA_ERF_EXACT
+                 : f == erf_fn::spline ? VRT_CUDA_APPROX_ERF_SPLINE
+                 : f == erf_fn::spline_mirror ? VRT_CUDA_APPROX_ERF_SPLINE_MIRROR
+                 : f == erf_fn::taylor ? VRT_CUDA_APPROX_ERF_TAYLOR
+                                       : VRT_CUDA_ERF_AS;
+        return flags;
+    }
+} // namespace cuda
+
 // ---- scalar entries: libm-class exp/erf, truncating quantisation (modes 1 and 5) -------------------------------------
 
 /// Drop-in for vrt::render_image<radiance<transmittance>>(w, h, image, cam, origin, gaussians, running)  (rt.h:227-247).

@@ -87,6 +87,14 @@ int main(int argc, char **argv)
                 ref_entries == st.list_entries ? "ok" : "FAIL");
     if (ref_entries != st.list_entries) ++failures;
 
+    // the <Exp, Erf> template arguments of tests/img-error.cpp:42-43 as flags: fast_exp + A&S erf, and the Taylor erf
+    simd_render_image<approx::simd_fast_exp, approx::simd_abramowitz_stegun_erf>(width, height, cpu, cam, origin, tiles, running, threads);
+    cuda_simd_render_image(width, height, gpu, cam, origin, tiles, running, threads, cuda::approx_flags(VRT_CUDA_MODE8, cuda::exp_fn::fast, cuda::erf_fn::as));
+    report("simd_render_image<simd_fast_exp, simd_abramowitz_stegun_erf> vs approx_flags(fast, as)", max_channel_diff(cpu, gpu, width * height), 2);
+    simd_render_image<approx::vcl_exp<sizeof(simd::Vec<simd::Float>)>, approx::simd_taylor_erf>(width, height, cpu, cam, origin, tiles, running, threads);
+    cuda_simd_render_image(width, height, gpu, cam, origin, tiles, running, threads, cuda::approx_flags(VRT_CUDA_MODE8, cuda::exp_fn::exact, cuda::erf_fn::taylor));
+    report("simd_render_image<vcl_exp, simd_taylor_erf>               vs approx_flags(exact, taylor)", max_channel_diff(cpu, gpu, width * height), 2);
+
     // the `running` convention: a render that starts with running == false reports "interrupted"
     const bool stopped = false;
     if (!cuda_simd_render_image(width, height, gpu, cam, origin, tiles, stopped, threads)) { std::printf("running=false must return true\n"); ++failures; }
