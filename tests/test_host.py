@@ -52,6 +52,27 @@ def test_struct_layouts_match_header(pkg):
     assert ctypes.sizeof(pkg._ffi.Stats) == 3 * 8 + 2 * 4 + 2 * 8 + 4 * 4 + 8
 
 
+def test_python_flag_values_match_header(pkg):
+    """The ctypes mirror (vrt.py) carries the flag and function-id values of include/vrt_cuda.h; evaluate the header's
+    #defines and compare every constant the mirror exposes."""
+    txt = open(os.path.join(ROOT, "include", "vrt_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    env = {}
+    for name, expr in re.findall(r"^#define (VRT_CUDA_\w+) (.+)$", txt, flags=re.M):
+        expr = re.sub(r"(\d+)u\b", r"\1", expr.strip())
+        env[name] = eval(expr, {}, env)  # noqa: S307 -- the header is ours; later defines refer to earlier ones
+    V = pkg.vrt
+    names = [n for n in dir(V) if n.isupper() and not n.startswith("_")]
+    checked = 0
+    for n in names:
+        if "VRT_CUDA_" + n in env:
+            assert getattr(V, n) == env["VRT_CUDA_" + n], n
+            checked += 1
+    assert checked >= 30, checked
+    for must in ("MODE1", "MODE4", "MODE5", "MODE8", "NO_SKIP", "DEPTH_WINDOW", "APPROX_ERF_TAYLOR", "APPROX_EXP_SPLINE", "FN_SPLINE_EXP", "LIST_BOUND"):
+        assert must in names and "VRT_CUDA_" + must in env, must
+
+
 def test_grid_scene_is_main_cpp_grid(pkg):
     g = pkg.scenes.grid(4)
     assert g.shape == (16, 10)
