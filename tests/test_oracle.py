@@ -227,3 +227,20 @@ def test_variant_radiance_matches_reference(gold_approx, pkg):
             got[i] = Oracle.radiance(scene[lists[t]], origin, dirs[k : k + 1], variant_code(erf, exp))[0]
         err = float(np.abs(got - gold_approx[key][sel]).max())
         assert err <= 2e-4, (key, err)
+
+
+def test_closed_form_transmittance_is_the_line_integral(pkg):
+    """What tests/transmittance.cpp plots: the closed form (rt.h:32-54) against a numerical integration of the density
+    along the ray (transmittance_step / density, rt.cpp:8-27) -- here with a fine step in float64, so the two must agree
+    closely: T(s) = exp(-int_0^s sum_j c_j exp(-|o + t n - mu_j|^2 / 2 sigma_j^2) dt)."""
+    tg = pkg.scenes.transmittance_test().astype(np.float64)
+    o, d = np.array([0, 0, -5.0]), np.array([0, 0, 1.0])
+    ks = np.arange(-6.0, 6.0001, 0.5)
+    s = (tg[2, 4:7] - o) @ d + ks * tg[2, 8]
+    got = Oracle.transmittance(tg.astype(np.float32), np.array([0, 0, -5, 0], np.float32), np.array([0, 0, 1, 0], np.float32), s.astype(np.float32), 0, f64=True)
+    for sk, T in zip(s, got):
+        t = np.linspace(0.0, sk, 20001)
+        pts = o[None, :] + t[:, None] * d[None, :]
+        dens = sum(g[9] * np.exp(-((pts - g[4:7]) ** 2).sum(1) / (2 * g[8] ** 2)) for g in tg)
+        want = np.exp(-np.trapezoid(dens, t))
+        assert abs(T - want) <= 2e-6, (sk, T, want)
