@@ -222,6 +222,10 @@ int vrt_cuda_mix_peak(vrt_cuda_ctx *ctx, int nf, int nm, int nl, double *steps_p
  * tabulation loops of tests/accuracy.cpp:16-52, and the way the parity tests pin every device approximation. */
 int vrt_cuda_approx_table(vrt_cuda_ctx *ctx, int fn, const float *x, float *y, uint64_t n);
 
+/* Throughput of one VRT_CUDA_FN_* device function in values per second (independent argument chains, no memory traffic):
+ * the GPU counterpart of tests/approx_cycles.cpp, which reports CPU cycles per value for the same functions. */
+int vrt_cuda_approx_rate(vrt_cuda_ctx *ctx, int fn, double *values_per_s_out);
+
 int vrt_cuda_sync(vrt_cuda_ctx *ctx);
 /* The context's cudaStream_t as an integer (for ordering NCCL / torch work after a render_device). */
 uint64_t vrt_cuda_stream(vrt_cuda_ctx *ctx);

@@ -73,6 +73,7 @@ CUDA_SYMBOLS = {
     "vrt_cuda_term_peak": (c_i, [vp, c_i, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_mix_peak": (c_i, [vp, c_i, c_i, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_approx_table": (c_i, [vp, c_i, vp, vp, c_u64]),
+    "vrt_cuda_approx_rate": (c_i, [vp, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_set_slice": (c_i, [vp, c_i]),
     "vrt_cuda_auto_slice": (c_i, [vp, c_d, ctypes.POINTER(c_i)]),
     "vrt_cuda_sync": (c_i, [vp]),

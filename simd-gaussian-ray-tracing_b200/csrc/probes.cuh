@@ -85,3 +85,52 @@ __global__ void __launch_bounds__(256) k_mix_peak(float *out, int iters, float a
     for (int i = 0; i < 16; ++i) t += v[i].x + v[i].y;
     if (t == 12345.678f) out[0] = t;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Throughput of the approximation functions (the GPU counterpart of tests/approx_cycles.cpp, which counts CPU cycles per
+// value with rdpmc): 8 independent argument chains per thread, each value nudges its own next argument so that nothing
+// can be hoisted, arguments stay in the function's interesting range.
+// ------------------------------------------------------------------------------------------------
+template <int FN>
+__device__ __forceinline__ float approx_fn(const ApproxTables &T, float x)
+{
+    switch (FN)
+    {
+    case VRT_CUDA_FN_SPLINE_ERF: return erf_approx<ERFV_SPLINE>(T, x);
+    case VRT_CUDA_FN_SPLINE_ERF_MIRROR: return erf_approx<ERFV_SPLINE_MIRROR>(T, x);
+    case VRT_CUDA_FN_TAYLOR_ERF: return erf_approx<ERFV_TAYLOR>(T, x);
+    case VRT_CUDA_FN_AS_ERF: return erf_approx<ERFV_AS>(T, x);
+    case VRT_CUDA_FN_ERF: return erf_approx<ERFV_EXACT>(T, x);
+    case VRT_CUDA_FN_EXP: return exp_approx<EXPV_EXACT>(T, x);
+    case VRT_CUDA_FN_FAST_EXP: return exp_approx<EXPV_FAST>(T, x);
+    default: return exp_approx<EXPV_SPLINE>(T, x);
+    }
+}
+
+template <int FN>
+__global__ void __launch_bounds__(256) k_approx_rate(float *out, int iters)
+{
+    __shared__ ApproxTables s_tab;
+    load_tables(s_tab);
+    constexpr bool is_exp = FN >= VRT_CUDA_FN_EXP;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        const float u = (float)((threadIdx.x * 8 + i) % 997) / 997.f; // [0, 1)
+        x[i] = is_exp ? -8.f * u : 5.f * u - 2.5f;
+    }
+    float acc = 0.f;
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            const float y = approx_fn<FN>(s_tab, x[i]);
+            acc += y;
+            x[i] = fmaf(y, is_exp ? -1e-4f : 1e-4f, x[i]);
+        }
+    }
+    if (acc == 12345.678f) out[0] = acc; // keeps the chains alive without a store in practice
+}
+

@@ -430,6 +430,12 @@ int dispatch_variant(vrt_cuda_ctx *ctx, const RenderArgs &a, int erfv, int expv)
     }
 }
 
+template <int FN>
+void launch_approx_rate(vrt_cuda_ctx *ctx, int blocks, int iters)
+{
+    k_approx_rate<FN><<<blocks, 256, 0, ctx->stream>>>((float *)ctx->counter.p, iters);
+}
+
 int upload_approx_tables(vrt_cuda_ctx *ctx)
 {
     ApproxTables t{};
@@ -598,6 +604,39 @@ int vrt_cuda_fp32_peak(vrt_cuda_ctx *ctx, int packed, double *tflops_out)
         if (rep > 0 && ms < best) best = ms;
     }
     *tflops_out = (double)blocks * threads * 16.0 * iters * 2.0 / (best * 1e-3) / 1e12;
+    return 0;
+}
+
+int vrt_cuda_approx_rate(vrt_cuda_ctx *ctx, int fn, double *values_per_s_out)
+{
+    if (!ctx || !values_per_s_out) return VRT_CUDA_E_INVALID;
+    if (fn < 0 || fn > VRT_CUDA_FN_SPLINE_EXP) return fail(ctx, VRT_CUDA_E_INVALID, "unknown function id %d", fn);
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
+    const int iters = 1024, blocks = ctx->sm_count * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep)
+    {
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        switch (fn)
+        {
+        case VRT_CUDA_FN_SPLINE_ERF: launch_approx_rate<VRT_CUDA_FN_SPLINE_ERF>(ctx, blocks, iters); break;
+        case VRT_CUDA_FN_SPLINE_ERF_MIRROR: launch_approx_rate<VRT_CUDA_FN_SPLINE_ERF_MIRROR>(ctx, blocks, iters); break;
+        case VRT_CUDA_FN_TAYLOR_ERF: launch_approx_rate<VRT_CUDA_FN_TAYLOR_ERF>(ctx, blocks, iters); break;
+        case VRT_CUDA_FN_AS_ERF: launch_approx_rate<VRT_CUDA_FN_AS_ERF>(ctx, blocks, iters); break;
+        case VRT_CUDA_FN_ERF: launch_approx_rate<VRT_CUDA_FN_ERF>(ctx, blocks, iters); break;
+        case VRT_CUDA_FN_EXP: launch_approx_rate<VRT_CUDA_FN_EXP>(ctx, blocks, iters); break;
+        case VRT_CUDA_FN_FAST_EXP: launch_approx_rate<VRT_CUDA_FN_FAST_EXP>(ctx, blocks, iters); break;
+        default: launch_approx_rate<VRT_CUDA_FN_SPLINE_EXP>(ctx, blocks, iters); break;
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *values_per_s_out = (double)blocks * 256.0 * 8.0 * iters / (best * 1e-3);
     return 0;
 }
 

@@ -207,6 +207,12 @@ class Renderer:
                     "vrt_cuda_approx_table")
         return out
 
+    def approx_rate(self, fn):
+        """values/s of one FN_* device function (the GPU counterpart of tests/approx_cycles.cpp)."""
+        out = ctypes.c_double()
+        self._check(self._lib.vrt_cuda_approx_rate(self._h, int(fn), ctypes.byref(out)), "vrt_cuda_approx_rate")
+        return float(out.value)
+
     def set_slice(self, slice_):
         self._check(self._lib.vrt_cuda_set_slice(self._h, int(slice_)), "vrt_cuda_set_slice")
 

@@ -190,3 +190,17 @@ def test_tables_against_compiled_reference_live(pkg, renderer):
         a, r = DEVICE_TOL[name]
         viol = float((np.abs(got.astype(np.float64) - want) - (a + r * np.abs(want))).max())
         assert viol <= 0, (name, viol)
+
+
+def test_function_throughput_probe(pkg, renderer):
+    """tests/approx_cycles.cpp counts CPU cycles per value of every approximation; vrt_cuda_approx_rate is its GPU
+    counterpart (values/s, register-resident argument chains).  Only sanity is asserted; the figures go to profiles/."""
+    V = pkg.vrt
+    ids = (V.FN_SPLINE_ERF, V.FN_SPLINE_ERF_MIRROR, V.FN_TAYLOR_ERF, V.FN_AS_ERF, V.FN_ERF, V.FN_EXP, V.FN_FAST_EXP, V.FN_SPLINE_EXP)
+    rates = {name: renderer.approx_rate(fn) for fn, name in zip(ids, APPROX_FNS)}
+    for name, r in rates.items():
+        print(f"{name}: {r:.3e} values/s")
+        assert 1e11 < r < 4e13, (name, r)
+    assert rates["fast_exp"] > rates["spline_exp"]  # two FMA-pipe ops and a conversion against an 18-knot search
+    with pytest.raises(V.VrtCudaError):
+        renderer.approx_rate(42)
