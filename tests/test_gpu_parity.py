@@ -457,6 +457,24 @@ def test_empty_scene_and_ragged_image(pkg, renderer):
     check(gpu_at(rad, pix, 100), ref, "ragged 100x52 image, 25x13 tiles")
 
 
+def test_scene_out_of_view_renders_black_in_every_list_mode(pkg, renderer):
+    """Gaussians that exist but are seen by no pixel (far off to the side, tiny sigma): the literal lists may name them,
+    the per-cell visible lists are empty, every mode returns an all-zero radiance and an opaque-black / zero-alpha image."""
+    V = pkg.vrt
+    scene = pkg.scenes.grid(4).copy()
+    scene[:, 4] += 500.0  # far outside the frustum
+    scene[:, 8] = 1e-3
+    cam, origin = V.camera_t.app(64, 64)
+    renderer.set_gaussians(scene)
+    for flags, tiles in ((V.MODE8, (4, 4)), (V.MODE5, (4, 4)), (V.MODE4, (1, 1)), (V.MODE1, (1, 1)),
+                         ((V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (4, 4)), (V.MODE8 | V.APPROX_ERF_TAYLOR, (4, 4))):
+        f = renderer.frame(cam.view_matrix, origin, 64, 64, flags, tiles)
+        img, rad, st = renderer.frame_render(f, True, True)
+        assert np.all(rad == 0), hex(flags)
+        assert np.all((img & 0x00FFFFFF) == 0), hex(flags)
+        assert st["terms_executed"] == 0
+
+
 # ---------------------------------------------------------------- BASELINE configs at full size
 def _full_size_case(pkg, renderer, scene, W, tiles, n_pix, seed):
     """Renders the full frame with the production lists and checks a pixel subsample against the fp64 unit-ray arbiter fed
