@@ -9,7 +9,11 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
  * VRT_CUDA_E_* code on failure (vrt_cuda_last_error() gives the text); nothing throws, exits or
  * falls back to a CPU implementation -- without a CUDA device vrt_cuda_create() fails.
- * One context drives one GPU and owns one stream; contexts are independent (one per rank).
+ * One context drives one GPU and owns one stream; contexts on different GPUs are independent (one per rank, or one
+ * host thread each as in the app's --gpus mode).  The frame geometry lives in the device's constant memory, so two
+ * contexts on the SAME GPU must not have frames in flight at the same time (tile + render of one, then the other).
+ * Limits: images up to 65536 x 65536 with at most 2^22 8x4-pixel cells (about 134 Mpixel) per frame, reference tiles
+ * per axis <= 1024, fewer than 2^31 Gaussians (device indices are 32-bit).
  */
 #ifndef VRT_CUDA_H
 #define VRT_CUDA_H

@@ -152,6 +152,9 @@ static uint32_t mode_flags(uint64_t mode)
     }
 }
 
+/// the scene as the packed floats the C ABI takes (gaussian_t is 10 floats, types.h:195-200); nullptr for an empty scene
+static float *aos(std::vector<vrt::gaussian_t> &g) { return g.empty() ? nullptr : &g[0].albedo.x; }
+
 static double now_ms()
 {
     struct timespec ts;
@@ -176,7 +179,7 @@ int main(int argc, char **argv)
     if (cmd.synthetic)
     {
         gaussians.resize(cmd.synthetic);
-        vrt_host_scene_synthetic(cmd.synthetic, cmd.seed, cmd.sig_lo, cmd.sig_hi, &gaussians[0].albedo.x);
+        vrt_host_scene_synthetic(cmd.synthetic, cmd.seed, cmd.sig_lo, cmd.sig_hi, aos(gaussians));
     }
     else if (cmd.infile != nullptr)
     {
@@ -187,13 +190,13 @@ int main(int argc, char **argv)
             return EXIT_FAILURE;
         }
         gaussians.resize(n);
-        vrt_host_read_obj(cmd.infile, &gaussians[0].albedo.x, n);
+        vrt_host_read_obj(cmd.infile, aos(gaussians), n);
     }
     else
     {
         const uint32_t dim = (uint8_t)cmd.grid_dim; // u8 in the reference
         gaussians.resize((size_t)dim * dim);
-        if (vrt_host_scene_grid(dim, dim ? &gaussians[0].albedo.x : nullptr) != (uint64_t)dim * dim)
+        if (vrt_host_scene_grid(dim, aos(gaussians)) != (uint64_t)dim * dim)
         {
             std::fprintf(stderr, "[ ERROR ]\tbad grid dimension\n");
             return EXIT_FAILURE;
@@ -201,12 +204,12 @@ int main(int argc, char **argv)
     }
 
     // ---- devices ----
-    const int n_gpus = (int)cmd.gpus;
+    const int n_gpus = cmd.gpus >= 1 && cmd.gpus <= 64 ? (int)cmd.gpus : 1;
     std::vector<vrt_cuda_ctx *> ctx(n_gpus, nullptr);
     for (int d = 0; d < n_gpus; ++d)
     {
         if (vrt_cuda_create(d, &ctx[d]) != VRT_CUDA_OK) DIE(nullptr, "vrt_cuda_create");
-        if (vrt_cuda_set_gaussians(ctx[d], &gaussians[0].albedo.x, gaussians.size()) != VRT_CUDA_OK) DIE(ctx[d], "vrt_cuda_set_gaussians");
+        if (vrt_cuda_set_gaussians(ctx[d], aos(gaussians), gaussians.size()) != VRT_CUDA_OK) DIE(ctx[d], "vrt_cuda_set_gaussians");
     }
 
     const uint32_t width = (uint32_t)cmd.w, height = (uint32_t)cmd.h;

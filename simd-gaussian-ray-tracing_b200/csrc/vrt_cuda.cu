@@ -180,6 +180,10 @@ int make_geom(vrt_cuda_ctx *ctx, const vrt_cuda_frame *f, int list_kind_override
     G.cpty = (G.tile_h + CELL_H - 1) / CELL_H;
     G.ncx = G.tiles_x * G.cptx;
     G.ncy = G.tiles_y * G.cpty;
+    // a work item packs the cell id into ITEM_CELL_BITS bits (k1_order / k2_render)
+    if ((uint64_t)G.ncx * (uint64_t)G.ncy > (1ull << ITEM_CELL_BITS))
+        return fail(ctx, VRT_CUDA_E_INVALID, "image %ux%u has more than %llu 8x4-pixel cells (about 134 Mpixel): render it in row bands of separate frames", f->width, f->height,
+                    1ull << ITEM_CELL_BITS);
     G.uniform = (G.tile_w % CELL_W == 0 && G.tile_h % CELL_H == 0) ? 1 : 0;
     G.slice = SLICE_MAX;
     G.row_begin = (int)f->row_begin;
@@ -562,7 +566,7 @@ static int set_gaussians_impl(vrt_cuda_ctx *ctx, const float *aos, uint64_t n, c
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
     if (n && !aos) return fail(ctx, VRT_CUDA_E_INVALID, "aos is NULL");
-    if (n > 0xFFFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "too many Gaussians");
+    if (n > 0x7FFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "too many Gaussians (device indices are 32-bit, cull records are addressed as 2 * index)");
     CU(cudaSetDevice(ctx->device));
     if (int rc = reserve(ctx, ctx->aos, std::max<size_t>(n, 1) * 40)) return rc;
     if (n) CU(cudaMemcpyAsync(ctx->aos.p, aos, n * 40, kind, ctx->stream));
@@ -893,7 +897,7 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
     if (int rc = make_geom(ctx, frame, 1, G, cxs, cys)) return rc;
     if (n_tiles != (uint64_t)G.tiles_x * G.tiles_y) return fail(ctx, VRT_CUDA_E_INVALID, "n_tiles %llu != tiles_x*tiles_y %d", (unsigned long long)n_tiles, G.tiles_x * G.tiles_y);
     const uint64_t total = offsets[n_tiles];
-    if (total > 0xFFFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "tile lists too long");
+    if (total > 0x7FFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "tile lists too long (device indices are 32-bit)");
     if (total && !aos_concat) return fail(ctx, VRT_CUDA_E_INVALID, "aos_concat is NULL");
     std::vector<uint32_t> off32(n_tiles + 1);
     for (uint64_t t = 0; t <= n_tiles; ++t)

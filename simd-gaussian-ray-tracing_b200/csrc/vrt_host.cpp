@@ -53,22 +53,24 @@ namespace
     }
 
     // ---- PNG (stored deflate) ----
-    uint32_t crc_table[256];
-    bool crc_ready = false;
-    uint32_t crc32(uint32_t crc, const uint8_t *p, size_t n)
+    struct CrcTable
     {
-        if (!crc_ready)
+        uint32_t t[256];
+        CrcTable()
         {
             for (uint32_t i = 0; i < 256; ++i)
             {
                 uint32_t c = i;
                 for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-                crc_table[i] = c;
+                t[i] = c;
             }
-            crc_ready = true;
         }
+    };
+    uint32_t crc32(uint32_t crc, const uint8_t *p, size_t n)
+    {
+        static const CrcTable table; // thread-safe one-time initialisation (the app writes frames from one thread, tests may not)
         crc = ~crc;
-        for (size_t i = 0; i < n; ++i) crc = crc_table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+        for (size_t i = 0; i < n; ++i) crc = table.t[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
         return ~crc;
     }
     void put32(std::vector<uint8_t> &v, uint32_t x)

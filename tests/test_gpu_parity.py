@@ -432,6 +432,9 @@ def test_errors_are_reported(pkg, renderer):
         renderer.tile(renderer.frame(cam.view_matrix, origin, 100, 100, V.MODE8, (16, 16)))  # 100 % 16 != 0
     with pytest.raises(V.VrtCudaError):
         renderer.tile(renderer.frame(np.zeros(16, np.float32), origin, 64, 64, V.MODE8, (4, 4)))  # singular view
+    with pytest.raises(V.VrtCudaError, match="cells"):
+        # more 8x4-pixel cells than a work item can name (rejected by the frame validation, before any launch)
+        renderer.tile(renderer.frame(cam.view_matrix, origin, 65536, 65536, V.MODE8, (16, 16)))
     f = renderer.frame(cam.view_matrix, origin, 96, 96, V.MODE8, (4, 4))
     renderer.tile(f)
     cam2, origin2 = V.camera_t.app(96, 96, rotation=10.0)
