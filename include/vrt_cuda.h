@@ -207,7 +207,8 @@ int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
  * renders are bit-identical only if they use the same slice.  slice = 0 (default) picks it per frame from the listed work;
  * a multi-GPU caller that wants its gathered bands to equal a single-GPU frame bit for bit asks for the automatic choice
  * of the FULL frame at its share of the work (vrt_cuda_auto_slice after a full-frame vrt_cuda_tile, share = 1 / ranks) and
- * sets it on every rank. */
+ * sets it on every rank.  A pinned slice also pins the emitter register block of the render kernel (8; otherwise chosen from
+ * the mean list length of the rendered band), the only other choice that regroups the sums. */
 int vrt_cuda_set_slice(vrt_cuda_ctx *ctx, int slice);
 int vrt_cuda_auto_slice(vrt_cuda_ctx *ctx, double share, int *slice_out);
 

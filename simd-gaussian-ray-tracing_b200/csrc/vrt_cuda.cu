@@ -350,7 +350,10 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     // sample chains per thread beats occupancy (tools/tune_k2.py); short lists waste less padding with Q = 4
     // mean list length over the lists that are actually rendered: a row band leaves the per-cell lists outside it empty
     const uint64_t lists_in_band = ctx->geom.list_kind == 0 ? (uint64_t)std::max(0, ctx->cy_end - ctx->cy_begin) * ctx->geom.ncx : ctx->n_lists;
-    const int q = ctx->tune_q ? ctx->tune_q : ((lists_in_band && ctx->n_entries / lists_in_band >= 24) ? 8 : 4);
+    // A pinned slice size (vrt_cuda_set_slice) says the caller composes one frame from bands rendered separately and wants
+    // them bit-identical to the whole frame: the emitter block must then not depend on the band's own lists either (a band of
+    // mean length 24.4 inside a frame of mean 23.6 once rendered with Q = 8 next to a Q = 4 frame: same sums, another grouping).
+    const int q = ctx->tune_q ? ctx->tune_q : ((ctx->tune_slice || (lists_in_band && ctx->n_entries / lists_in_band >= 24)) ? 8 : 4);
     const bool p = ctx->tune_pack != 0;
     if (a.window)
     {

@@ -20,7 +20,26 @@ def pkg():
     need = [os.path.join(ge.PKG_DIR, "csrc", n) for n in ("libvrt_cuda.so", "libvrt_host.so")] + [os.path.join(ROOT, "oracle", "libvrt_oracle.so")]
     if not all(os.path.exists(p) for p in need):
         ge.build()
-    return ge.load_package()
+    pkg_ = ge.load_package()
+    if os.environ.get("VRT_EMU") == "1":
+        _use_emulated_library(pkg_)
+    return pkg_
+
+
+def _use_emulated_library(pkg_):
+    """VRT_EMU=1 (set only by tests/test_emu.py for its child pytest run): the `gpu` tests execute on the CPU against
+    tests/emu/_build/libvrt_cuda_emu.so -- the product's CUDA sources compiled against the SIMT interpreter of
+    tests/emu/cuda_emu.h.  Test infrastructure: the package itself never loads that library."""
+    import ctypes
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+
+    lib = ctypes.CDLL(build_emu.build())
+    for sym, (res, args) in pkg_._ffi.CUDA_SYMBOLS.items():
+        fn = getattr(lib, sym)
+        fn.restype, fn.argtypes = res, args
+    pkg_._ffi._cuda = lib
 
 
 @pytest.fixture(scope="session")

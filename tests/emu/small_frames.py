@@ -1,0 +1,140 @@
+"""Small-frame versions of the heavier `gpu` parity tests, sized for the SIMT interpreter (TEST INFRASTRUCTURE; run by
+tests/test_emu.py in its VRT_EMU=1 child pytest, through the same C ABI, oracle and tolerances as tests/test_gpu_parity.py).
+
+They reach the code paths the quick gpu tests do not touch at interpreter-friendly sizes: the depth-window kernel and its
+long-list fall-back, cells split into emitter slices (+ the combine pass), lists walked as contiguous record ranges through
+the bulk-copy / mbarrier staging with more than one chunk in flight, and the register-block / packing variants.
+The file is not collected by a plain `pytest tests/` (its name does not match test_*.py); it also passes on a GPU.
+"""
+import numpy as np
+import pytest
+from parity_util import channel_diff_lsb, oracle_radiance, reference_lists
+from test_gpu_parity import all_pixels, check, gpu_at
+
+pytestmark = pytest.mark.gpu
+
+
+def bound_flags(V, erf=0):
+    return (((V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND) & ~1) | erf
+
+
+@pytest.mark.parametrize("erf", [0, 1])
+def test_depth_window_small(pkg, renderer, erf):
+    """Depth-window mode reproduces the plain evaluation and resolves most terms by saturation (k2_window)."""
+    V = pkg.vrt
+    W = 96
+    scene = pkg.scenes.synthetic(2500, 21, -1.9, -1.4)
+    cam, origin = V.camera_t.app(W, W, rotation=12.0)
+    renderer.set_gaussians(scene)
+    f0 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf), (12, 12), 6.0)
+    img0, rad0, st0 = renderer.frame_render(f0, True, True)
+    f1 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf) | V.DEPTH_WINDOW, (12, 12), 6.0)
+    img1, rad1, st1 = renderer.frame_render(f1, True, True)
+    assert float(np.abs(rad0 - rad1).max()) <= 2e-5
+    assert channel_diff_lsb(img0, img1) <= 1
+    assert st1["terms_listed"] == st0["terms_listed"] and st0["terms_saturated"] == 0
+    assert abs(st1["terms_executed"] + st1["terms_saturated"] - st0["terms_executed"]) <= 1e-2 * st0["terms_executed"]
+    assert 0 < st1["terms_saturated"] and st1["terms_executed"] < st0["terms_executed"]
+    pix = all_pixels(W, W, 53)
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1 - erf, f64="unit", near_sigmas=12)
+    check(gpu_at(rad1, pix, W), ideal, f"depth-window mode vs arbiter (erf {erf})")
+
+
+def test_depth_window_long_lists_take_the_in_loop_test(pkg, renderer):
+    """Lists longer than the window kernel's per-warp cache (160 entries) go to k2_render's in-loop saturation test; a frame
+    that mixes both kinds must still be the plain image."""
+    V = pkg.vrt
+    W = 32
+    scene = pkg.scenes.synthetic(2000, 9, -1.0, -0.7)  # wide Gaussians: every cell lists hundreds
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    f0 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V), (4, 4), 6.0)
+    _, rad0, st0 = renderer.frame_render(f0, False, True)
+    assert st0["max_list"] > 160
+    f1 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V) | V.DEPTH_WINDOW, (4, 4), 6.0)
+    _, rad1, st1 = renderer.frame_render(f1, False, True)
+    assert float(np.abs(rad0 - rad1).max()) <= 1e-4 * max(1.0, float(rad0.max()))
+    assert st1["terms_saturated"] > 0
+
+
+def test_split_cells_and_bands_small(pkg, renderer):
+    """Heavy cells split into emitter slices: same image for every slice size (up to fp32 regrouping), bands of one slice
+    size compose bit-exactly to the whole frame, parity against the oracle."""
+    V = pkg.vrt
+    W = 64
+    scene = pkg.scenes.synthetic(900, 5, -1.3, -1.0)
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    flags = bound_flags(V)
+    f = renderer.frame(cam.view_matrix, origin, W, W, flags, (8, 8))
+    try:
+        renderer.set_slice(8)
+        img, rad, st = renderer.frame_render(f, True, True)
+        assert st["slice"] == 8 and st["max_list"] > 24  # lists longer than 3 slices: split cells exist
+        img2, rad2 = np.zeros_like(img), np.zeros_like(rad)
+        for rows in ((0, 24), (24, 40), (40, 64)):
+            fb = renderer.frame(cam.view_matrix, origin, W, W, flags, (8, 8), rows=rows)
+            renderer.tile(fb)
+            renderer.render(fb, True, True, image=img2, radiance=rad2)
+        assert np.array_equal(img, img2) and np.array_equal(rad, rad2)
+        for s in (16, 64):
+            renderer.set_slice(s)
+            _, rad3, st3 = renderer.frame_render(f, False, True)
+            assert st3["slice"] == s and float(np.abs(rad3 - rad).max()) <= 2e-5 * max(1.0, float(rad.max()))
+    finally:
+        renderer.set_slice(0)
+    pix = all_pixels(W, W, 29)
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1, f64="unit", near_sigmas=12)
+    check(gpu_at(rad, pix, W), ideal, "split cells vs arbiter")
+
+
+def test_contiguous_lists_through_the_bulk_copy_staging(pkg, renderer):
+    """NO_SKIP walks the ALL list and caller-supplied tiles_t lists as contiguous record ranges: several 32-record chunks per
+    list, double-buffered bulk copies completing on per-warp mbarriers.  Must equal the culled evaluation and the oracle."""
+    V = pkg.vrt
+    W = 32
+    scene = pkg.scenes.synthetic(150, 3, -1.2, -0.9)
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    # untiled: one list of 150 records = 5 chunks
+    f_all = renderer.frame(cam.view_matrix, origin, W, W, V.MODE4 | V.NO_SKIP)
+    _, rad_all, st_all = renderer.frame_render(f_all, False, True)
+    assert st_all["terms_executed"] == st_all["terms_listed"] == 5.0 * 150 * 150 * W * W
+    f_cull = renderer.frame(cam.view_matrix, origin, W, W, V.MODE4)
+    _, rad_cull, st_cull = renderer.frame_render(f_cull, False, True)
+    assert st_cull["terms_executed"] <= st_all["terms_executed"]
+    assert float(np.abs(rad_all - rad_cull).max()) <= 2e-5 * max(1.0, float(rad_all.max()))
+    pix = all_pixels(W, W, 7)
+    ref = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1)
+    check(gpu_at(rad_all, pix, W), ref, "ALL list, literal walk (bulk-copy staging)")
+    # tiled: the reference's own lists handed over as a tiles_t, walked literally
+    lists = reference_lists(scene, cam.view_matrix, 4)
+    assert max(len(l) for l in lists) > 32
+    f_t = renderer.frame(cam.view_matrix, origin, W, W, V.MODE8 | V.NO_SKIP, (4, 4))
+    renderer.set_tile_lists(f_t, [scene[l] for l in lists])
+    _, rad_t, st_t = renderer.render(f_t, False, True)
+    assert st_t["terms_executed"] == st_t["terms_listed"]
+    ref_t = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1, tiles=4, lists=lists)
+    check(gpu_at(rad_t, pix, W), ref_t, "tiles_t lists, literal walk (bulk-copy staging)")
+
+
+def test_register_block_and_packing_variants_small(pkg, renderer):
+    """Q = 4 / 8, packed / scalar arithmetic and the exact-erf kernels all evaluate the same sums."""
+    V = pkg.vrt
+    W = 48
+    scene = pkg.scenes.synthetic(400, 11, -1.4, -1.0)
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    for erf in (0, 1):
+        f = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf), (6, 6))
+        _, base, _ = renderer.frame_render(f, False, True)
+        try:
+            for q, p in ((4, 0), (4, 1), (8, 1), (8, 0), (0, 2)):
+                renderer.set_tuning(q, p)
+                _, r, _ = renderer.frame_render(f, False, True)
+                assert float(np.abs(r - base).max()) <= 2e-5 * max(1.0, float(base.max())), (erf, q, p)
+        finally:
+            renderer.set_tuning(0, 1)
+        pix = all_pixels(W, W, 31)
+        ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1 - erf, f64="unit", near_sigmas=12)
+        check(gpu_at(base, pix, W), ideal, f"bounded lists vs arbiter (erf {erf})")

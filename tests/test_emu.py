@@ -1,0 +1,116 @@
+"""CPU execution of the product's CUDA sources under the SIMT interpreter of tests/emu (TEST INFRASTRUCTURE).
+
+The container that runs `pytest -m "not gpu"` has no GPU, so without this file the kernels and their launch logic would
+only ever be exercised on the B200 box.  tests/emu/build_emu.py compiles a rewritten COPY of
+simd-gaussian-ray-tracing_b200/csrc/{vrt_cuda.cu,*.cuh} against tests/emu/cuda_emu.h (every CUDA thread a fiber, warp
+collectives and __syncthreads as rendezvous, guarded device allocations, an mbarrier / bulk-copy model) into
+tests/emu/_build/libvrt_cuda_emu.so, and this file runs a selection of the `gpu` parity tests against that library in a
+child pytest (VRT_EMU=1, see tests/conftest.py) -- the same test functions, the same oracle, the same tolerances, through
+the same C ABI.  The interpreter aborts on divergent collectives, deadlocks, __trap, writes outside an allocation and
+bulk copies nobody waits for, so those show up here as failures too.
+
+This is not a product path and not a fallback: nothing under simd-gaussian-ray-tracing_b200/ can load the emulated
+library (the package binds csrc/libvrt_cuda.so only and fails without a GPU), and numbers produced here are never
+reported as measurements.  Arithmetic differs from the GPU by a few ulp (no MUFU approximations, no FMA contraction), so
+the GPU run at round end stays the parity gate; this run pins the LOGIC (indexing, lists, queues, bands, split cells,
+staging) at small sizes.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+# gpu tests small enough for the interpreter (a frame of 256 x 256 pixels takes about a second); the full-size frames
+# of BASELINE configs 2-5, the app binary (linked against the real library) and the throughput probes stay GPU-only
+EMU_SELECTION = [
+    "tests/test_gpu_parity.py::test_config1_tiled",
+    "tests/test_gpu_parity.py::test_config1_untiled",
+    "tests/test_gpu_parity.py::test_config1_against_compiled_reference",
+    "tests/test_gpu_parity.py::test_membership_config1",
+    "tests/test_gpu_parity.py::test_membership_img_error_scene",
+    "tests/test_gpu_parity.py::test_membership_grid64_and_rotated",
+    "tests/test_gpu_parity.py::test_membership_objects",
+    "tests/test_gpu_parity.py::test_row_bands_compose",
+    "tests/test_gpu_parity.py::test_bound_mode_matches_all",
+    "tests/test_gpu_parity.py::test_bounded_lists_are_conservative_and_tight",
+    "tests/test_gpu_parity.py::test_errors_are_reported",
+    "tests/test_gpu_parity.py::test_empty_scene_and_ragged_image",
+    "tests/test_gpu_parity.py::test_scene_out_of_view_renders_black_in_every_list_mode",
+    "tests/test_gpu_approx.py::test_tables_match_reference",
+    "tests/test_gpu_approx.py::test_variants_on_device_built_lists",
+    "tests/test_gpu_approx.py::test_variant_errors",
+    "tests/test_gpu_approx.py::test_tables_against_compiled_reference_live",
+    # the heavier paths at interpreter-friendly sizes: depth window, split cells, bulk-copy staging, kernel variants
+    "tests/emu/small_frames.py",
+]
+# gpu tests that also pass under the interpreter but take minutes there (VRT_EMU_FULL=1 adds them): OBJ scenes, the
+# img-error procedure, thin bands of a dense frame, the 512^2 depth-window frames, the NO_SKIP walk of the monkey
+EMU_SLOW = [
+    "tests/test_gpu_parity.py::test_objects_tiled",
+    "tests/test_gpu_parity.py::test_teapot_subsample",
+    "tests/test_gpu_parity.py::test_host_tile_lists_equal_device_lists",
+    "tests/test_gpu_parity.py::test_thin_bands_of_a_dense_frame_compose_bit_exactly",
+    "tests/test_gpu_parity.py::test_depth_window_mode_is_the_same_image",
+]
+
+
+@pytest.fixture(scope="module")
+def build_emu():
+    import build_emu as b
+
+    return b
+
+
+def test_interpreter_selftest(build_emu):
+    """Known answers for the collectives / barrier / atomics / bulk-copy model, and the interpreter's own checks: each of
+    the deliberately broken kernels of tests/emu/selftest.cu must abort with its diagnosis."""
+    lib = build_emu.build_selftest()
+    assert ctypes.CDLL(lib).emu_selftest(0) == 0
+    expect = {1: "write outside a device allocation", 2: "divergent collectives", 3: "deadlock", 4: "never waited for"}
+    for case, message in expect.items():
+        r = subprocess.run([sys.executable, "-c", f"import ctypes; ctypes.CDLL({lib!r}).emu_selftest({case})"], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and message in r.stderr, (case, r.returncode, r.stderr[-500:])
+
+
+def test_translation_covers_every_cuda_construct(build_emu):
+    """The rewrite must account for every launch and every inline-PTX statement of the product sources (it raises on
+    anything it does not know), and must leave the product tree untouched."""
+    csrc = build_emu.CSRC
+    n_launch = n_asm = 0
+    for f in build_emu.sources():
+        src = open(os.path.join(csrc, f)).read()
+        out = build_emu.translate(f, src)
+        n_launch += src.count("<<<")
+        n_asm += len(__import__("re").findall(r"\basm\b", src))
+        assert out.count("emu::launch(") == src.count("<<<"), f
+    assert n_launch >= 30 and n_asm >= 8
+    assert not any("emu" in f.lower() for f in os.listdir(csrc)), "emulation artefacts do not belong in the product tree"
+
+
+def test_package_cannot_load_the_emulated_library(pkg):
+    """The product binding names csrc/libvrt_cuda.so and nothing else."""
+    src = open(os.path.join(ROOT, "simd-gaussian-ray-tracing_b200", "_ffi.py")).read()
+    assert "libvrt_cuda.so" in src and "emu" not in src.lower()
+    assert os.path.realpath(pkg._ffi.cuda_lib()._name) == os.path.realpath(os.path.join(ROOT, "simd-gaussian-ray-tracing_b200", "csrc", "libvrt_cuda.so"))
+
+
+@pytest.mark.parametrize("tma", ["lazy", "eager"])
+def test_gpu_parity_tests_under_the_interpreter(build_emu, tma):
+    """The selected `gpu` tests, unchanged, against the emulated library.  Bulk copies complete either at the first wait on
+    their mbarrier (lazy: a consumer that forgets to wait reads stale data) or at issue (eager: a producer that refills a
+    buffer still being read clobbers it); the TMA-staged paths must pass under both."""
+    build_emu.build()
+    selection = EMU_SELECTION if tma == "lazy" else ["tests/emu/small_frames.py::test_contiguous_lists_through_the_bulk_copy_staging", "tests/test_gpu_parity.py::test_config1_untiled"]
+    if tma == "lazy" and os.environ.get("VRT_EMU_FULL") == "1":
+        selection = selection + EMU_SLOW
+    env = dict(os.environ, VRT_EMU="1", VRT_EMU_TMA=tma)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", *selection], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=1500)
+    tail = r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout, tail
