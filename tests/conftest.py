@@ -35,7 +35,8 @@ def _use_emulated_library(pkg_):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
 
-    lib = ctypes.CDLL(build_emu.build())
+    # VRT_EMU_LIB: an alternative build of the same translation (e.g. -fsanitize=address, run under LD_PRELOAD=libasan.so)
+    lib = ctypes.CDLL(os.environ.get("VRT_EMU_LIB") or build_emu.build())
     for sym, (res, args) in pkg_._ffi.CUDA_SYMBOLS.items():
         fn = getattr(lib, sym)
         fn.restype, fn.argtypes = res, args

@@ -160,31 +160,43 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh") or f == "vrt_cuda.cu")
 
 
-def build(force=False):
-    """Translate + compile if the product sources (or the interpreter) changed; returns the library path."""
-    os.makedirs(BUILD, exist_ok=True)
+def build(force=False, asan=False):
+    """Translate + compile if the product sources (or the interpreter) changed; returns the library path.
+    asan=True: the same translation with -fsanitize=address into _build/asan/ (load it in a process started with
+    LD_PRELOAD=libasan.so): out-of-bounds READS and writes of the kernels and the host code abort with the source line."""
+    out_dir = os.path.join(BUILD, "asan") if asan else BUILD
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, "libvrt_cuda_emu.so")
     h = hashlib.sha256()
     inputs = [os.path.join(CSRC, f) for f in sources()] + [os.path.join(HERE, f) for f in ("cuda_emu.h", "cuda_emu.cpp", "build_emu.py")]
     inputs += [os.path.join(ROOT, "include", f) for f in ("vrt_cuda.h", "vrt_approx_tables.h")]
     for p in inputs:
         h.update(open(p, "rb").read())
-    stamp = os.path.join(BUILD, "stamp")
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
-        return LIB
+    stamp = os.path.join(out_dir, "stamp")
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return lib
     for f in sources():
         out = translate(f, open(os.path.join(CSRC, f)).read())
         dst = "vrt_cuda_emu.cpp" if f == "vrt_cuda.cu" else f
-        with open(os.path.join(BUILD, dst), "w") as fh:
+        with open(os.path.join(out_dir, dst), "w") as fh:
             fh.write(f"// GENERATED by tests/emu/build_emu.py from simd-gaussian-ray-tracing_b200/csrc/{f} -- test infrastructure, do not edit\n" + out)
-    cmd = ["g++", "-std=c++17", "-O2", "-g", "-march=x86-64-v3", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
-           "-I", BUILD, "-I", HERE, "-I", os.path.join(ROOT, "include"),
-           "-o", LIB, os.path.join(BUILD, "vrt_cuda_emu.cpp"), os.path.join(HERE, "cuda_emu.cpp")]
+    opt = ["-O1", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else ["-O2"]
+    cmd = ["g++", "-std=c++17", *opt, "-g", "-march=x86-64-v3", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
+           "-I", out_dir, "-I", HERE, "-I", os.path.join(ROOT, "include"),
+           "-o", lib, os.path.join(out_dir, "vrt_cuda_emu.cpp"), os.path.join(HERE, "cuda_emu.cpp")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulated build failed:\n" + r.stdout[-6000:])
     with open(stamp, "w") as fh:
         fh.write(h.hexdigest())
-    return LIB
+    return lib
+
+
+def libasan():
+    """path of the AddressSanitizer runtime of this g++ (to LD_PRELOAD), or None"""
+    r = subprocess.run(["g++", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True)
+    p = r.stdout.strip()
+    return p if r.returncode == 0 and os.path.isabs(p) and os.path.exists(p) else None
 
 
 def build_selftest():

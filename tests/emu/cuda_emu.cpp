@@ -85,7 +85,11 @@ std::vector<PendingCopy> g_pending;
 bool g_tma_lazy = true;
 
 // guarded allocations: [guard | payload | guard]
+#ifdef __SANITIZE_ADDRESS__
+constexpr size_t GUARD = 0; // an AddressSanitizer build: its own red zones sit right at the block edges and also catch reads
+#else
 constexpr size_t GUARD = 256;
+#endif
 constexpr unsigned char GUARD_BYTE = 0xE7, FRESH_BYTE = 0xA5;
 std::map<void *, size_t> g_allocs;
 char g_last_error[256] = "";

@@ -114,3 +114,27 @@ def test_gpu_parity_tests_under_the_interpreter(build_emu, tma):
     tail = r.stdout[-3000:] + r.stderr[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout, tail
+
+
+def test_kernels_under_address_sanitizer(build_emu):
+    """The same translation built with -fsanitize=address: device buffers are plain heap blocks there, so a kernel (or the
+    launch logic) that reads or writes one element past a list, a queue, a record array or the image aborts with the source
+    line.  Ragged images, empty scenes, row bands, split cells, the depth window and the bulk-copy staging are the index
+    arithmetic most likely to be off by one."""
+    asan = build_emu.libasan()
+    if asan is None:
+        pytest.skip("this g++ has no libasan.so")
+    lib = build_emu.build(asan=True)
+    small = "tests/emu/small_frames.py::"
+    selection = [small + "test_depth_window_small", small + "test_split_cells_and_bands_small", small + "test_contiguous_lists_through_the_bulk_copy_staging",
+                 "tests/test_gpu_parity.py::test_empty_scene_and_ragged_image", "tests/test_gpu_parity.py::test_row_bands_compose",
+                 "tests/test_gpu_parity.py::test_scene_out_of_view_renders_black_in_every_list_mode"]
+    if os.environ.get("VRT_EMU_FULL") == "1":
+        selection += [small + "test_depth_window_long_lists_take_the_in_loop_test", small + "test_register_block_and_packing_variants_small",
+                      "tests/test_gpu_parity.py::test_config1_untiled", "tests/test_gpu_approx.py::test_variants_on_device_built_lists"]
+    env = dict(os.environ, VRT_EMU="1", VRT_EMU_LIB=lib, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", *selection], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=1500)
+    tail = r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
