@@ -138,3 +138,9 @@ def test_kernels_under_address_sanitizer(build_emu):
     tail = r.stdout[-3000:] + r.stderr[-3000:]
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
+    # randomised frames (tests/emu/fuzz_frames.py): odd image sizes, list lengths around the 32-record staging chunks, every
+    # list mode, NO_SKIP / depth window / pinned slice / emitter block, arbitrary row bands -- against the oracle, under ASan
+    cases = "400" if os.environ.get("VRT_EMU_FULL") == "1" else "60"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_frames.py"), "--emu", "--cases", cases, "--seed", "3"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-3000:]
