@@ -1,5 +1,5 @@
-"""Randomised small frames through the C ABI against the oracle (TEST INFRASTRUCTURE; run by tests/test_emu.py under the SIMT
-interpreter, by hand also on a GPU: `python tests/emu/fuzz_frames.py --cases 200 [--emu] [--seed 1]`).
+"""Randomised small frames through the C ABI against the oracle (run by tests/test_gpu_small_frames.py on the GPU and by tests/test_emu.py under the
+SIMT interpreter; by hand: `python tests/emu/fuzz_frames.py --cases 200 [--emu] [--seed 1]`).
 
 Every case draws an image size (any width / height, not multiples of the 8x4 cell), a tile count that divides it, a scene
 size around the staging boundaries (0, 1, 31, 32, 33, 64, 65, ...), a list mode, an erf variant, optional NO_SKIP /

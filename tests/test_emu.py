@@ -46,7 +46,7 @@ EMU_SELECTION = [
     "tests/test_gpu_approx.py::test_variant_errors",
     "tests/test_gpu_approx.py::test_tables_against_compiled_reference_live",
     # the heavier paths at interpreter-friendly sizes: depth window, split cells, bulk-copy staging, kernel variants
-    "tests/emu/small_frames.py",
+    "tests/test_gpu_small_frames.py",
 ]
 # gpu tests that also pass under the interpreter but take minutes there (VRT_EMU_FULL=1 adds them): OBJ scenes, the
 # img-error procedure, thin bands of a dense frame, the 512^2 depth-window frames, the NO_SKIP walk of the monkey
@@ -105,12 +105,13 @@ def test_gpu_parity_tests_under_the_interpreter(build_emu, tma):
     their mbarrier (lazy: a consumer that forgets to wait reads stale data) or at issue (eager: a producer that refills a
     buffer still being read clobbers it); the TMA-staged paths must pass under both."""
     build_emu.build()
-    selection = EMU_SELECTION if tma == "lazy" else ["tests/emu/small_frames.py::test_contiguous_lists_through_the_bulk_copy_staging", "tests/test_gpu_parity.py::test_config1_untiled"]
+    selection = EMU_SELECTION if tma == "lazy" else ["tests/test_gpu_small_frames.py::test_contiguous_lists_through_the_bulk_copy_staging", "tests/test_gpu_parity.py::test_config1_untiled"]
     if tma == "lazy" and os.environ.get("VRT_EMU_FULL") == "1":
         selection = selection + EMU_SLOW
     env = dict(os.environ, VRT_EMU="1", VRT_EMU_TMA=tma)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", *selection], cwd=ROOT, env=env, capture_output=True, text=True,
-                       timeout=1500)
+    # (the randomised sweep runs in the AddressSanitizer test below, with fewer cases)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "--deselect",
+                        "tests/test_gpu_small_frames.py::test_randomised_small_frames", *selection], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout and "skipped" not in r.stdout, tail
@@ -125,7 +126,7 @@ def test_kernels_under_address_sanitizer(build_emu):
     if asan is None:
         pytest.skip("this g++ has no libasan.so")
     lib = build_emu.build(asan=True)
-    small = "tests/emu/small_frames.py::"
+    small = "tests/test_gpu_small_frames.py::"
     selection = [small + "test_depth_window_small", small + "test_split_cells_and_bands_small", small + "test_contiguous_lists_through_the_bulk_copy_staging",
                  "tests/test_gpu_parity.py::test_empty_scene_and_ragged_image", "tests/test_gpu_parity.py::test_row_bands_compose",
                  "tests/test_gpu_parity.py::test_scene_out_of_view_renders_black_in_every_list_mode"]

@@ -1,11 +1,14 @@
-"""Small-frame versions of the heavier `gpu` parity tests, sized for the SIMT interpreter (TEST INFRASTRUCTURE; run by
-tests/test_emu.py in its VRT_EMU=1 child pytest, through the same C ABI, oracle and tolerances as tests/test_gpu_parity.py).
+"""Small frames through the C ABI against the oracle: the heavier code paths at sizes that take milliseconds on the GPU and
+seconds under the SIMT interpreter of tests/emu (tests/test_emu.py runs this file there too, VRT_EMU=1).
 
-They reach the code paths the quick gpu tests do not touch at interpreter-friendly sizes: the depth-window kernel and its
-long-list fall-back, cells split into emitter slices (+ the combine pass), lists walked as contiguous record ranges through
-the bulk-copy / mbarrier staging with more than one chunk in flight, and the register-block / packing variants.
-The file is not collected by a plain `pytest tests/` (its name does not match test_*.py); it also passes on a GPU.
+They reach what the quick parity tests do not: the depth-window kernel and its long-list fall-back, cells split into emitter
+slices (+ the combine pass) whose bands must compose bit-exactly, lists walked as contiguous record ranges through the
+bulk-copy / mbarrier staging with several chunks in flight, the register-block / packing variants, and a randomised sweep
+over image sizes, list lengths around the 32-record staging chunks, list modes, flags and row bands (tests/emu/fuzz_frames.py).
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 from parity_util import channel_diff_lsb, oracle_radiance, reference_lists
@@ -138,3 +141,18 @@ def test_register_block_and_packing_variants_small(pkg, renderer):
         pix = all_pixels(W, W, 31)
         ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1 - erf, f64="unit", near_sigmas=12)
         check(gpu_at(base, pix, W), ideal, f"bounded lists vs arbiter (erf {erf})")
+
+
+def test_randomised_small_frames(pkg, renderer):
+    """120 random frames (odd image sizes, 0..130 Gaussians, every list mode, NO_SKIP / depth window / pinned slice /
+    emitter block, arbitrary row bands): radiance of every band pixel within 1e-3 of the oracle, rows outside the band
+    untouched, packed pixels consistent with the radiance (tests/emu/fuzz_frames.py, seed 5)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import fuzz_frames
+
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for _ in range(120):
+        _, err = fuzz_frames.run_case(pkg, renderer, rng)
+        worst = max(worst, err)
+    print(f"worst max-abs radiance error over 120 random frames: {worst:.3e}")
