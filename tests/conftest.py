@@ -41,6 +41,15 @@ def _use_emulated_library(pkg_):
         fn = getattr(lib, sym)
         fn.restype, fn.argtypes = res, args
     pkg_._ffi._cuda = lib
+    # child processes (the volumetric-ray-tracer binary of tests/test_gpu_app.py) resolve the C ABI from the same library
+    os.environ["LD_PRELOAD"] = ":".join(p for p in (os.environ.get("LD_PRELOAD"), lib._name) if p)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _emulation_for_tests_without_fixtures(request):
+    """Under VRT_EMU=1 also the tests that only start the app binary need the library switch (LD_PRELOAD for children)."""
+    if os.environ.get("VRT_EMU") == "1":
+        request.getfixturevalue("pkg")
 
 
 @pytest.fixture(scope="session")

@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 
 # gpu tests small enough for the interpreter (a frame of 256 x 256 pixels takes about a second); the full-size frames
-# of BASELINE configs 2-5, the app binary (linked against the real library) and the throughput probes stay GPU-only
+# of BASELINE configs 2-5 and the throughput probes stay GPU-only
 EMU_SELECTION = [
     "tests/test_gpu_parity.py::test_config1_tiled",
     "tests/test_gpu_parity.py::test_config1_untiled",
@@ -47,6 +47,9 @@ EMU_SELECTION = [
     "tests/test_gpu_approx.py::test_tables_against_compiled_reference_live",
     # the heavier paths at interpreter-friendly sizes: depth window, split cells, bulk-copy staging, kernel variants
     "tests/test_gpu_small_frames.py",
+    # the callers either side of the path: the volumetric-ray-tracer binary and the C++ drop-in check built against the
+    # reference's own types resolve the C ABI from the interpreter build through LD_PRELOAD (tests/conftest.py)
+    "tests/test_gpu_app.py",
 ]
 # gpu tests that also pass under the interpreter but take minutes there (VRT_EMU_FULL=1 adds them): OBJ scenes, the
 # img-error procedure, thin bands of a dense frame, the 512^2 depth-window frames, the NO_SKIP walk of the monkey
