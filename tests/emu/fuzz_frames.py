@@ -20,19 +20,30 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
 SIZES = [0, 1, 2, 7, 31, 32, 33, 63, 64, 65, 97, 130]
 
 
+def tile_lists(scene, view, tx, ty):
+    """vrt::tile_gaussians(2/tx, 2/ty, scene, view) restated by the oracle: one index array per tile, row-major, y outer"""
+    from oracle_lib import Oracle
+
+    w, h, counts, idx = Oracle.tile_membership(np.float32(2.0) / np.float32(tx), np.float32(2.0) / np.float32(ty), scene, view)
+    assert (w, h) == (tx, ty) and len(counts) == tx * ty, (w, h, tx, ty)
+    offs = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    return [idx[offs[t] : offs[t + 1]] for t in range(tx * ty)]
+
+
 def run_case(pkg, renderer, rng, verbose=False):
-    from parity_util import oracle_radiance, pack_image, channel_diff_lsb, reference_lists
+    from parity_util import oracle_radiance, pack_image, channel_diff_lsb
 
     V = pkg.vrt
-    tiles = int(rng.choice([1, 1, 2, 3, 4, 5, 8]))
-    W, H = tiles * int(rng.integers(1, max(2, 72 // tiles))), tiles * int(rng.integers(1, max(2, 56 // tiles)))
+    tx, ty = int(rng.choice([1, 1, 2, 3, 4, 5, 8])), int(rng.choice([1, 1, 2, 3, 4, 5, 8]))  # reference tiles per axis, not square
+    W, H = tx * int(rng.integers(1, max(2, 72 // tx))), ty * int(rng.integers(1, max(2, 56 // ty)))
     n = int(rng.choice(SIZES))
     scene = pkg.scenes.synthetic(n, int(rng.integers(1, 1 << 30)), -1.3, -0.8) if n else np.zeros((0, 10), np.float32)
     cam, origin = V.camera_t.app(W, H, rotation=float(rng.uniform(-40, 40)))
     erf = int(rng.integers(0, 2))
     kind = str(rng.choice(["all", "bound", "reference", "reference_bound", "host_lists"]))
     tiled = kind in ("reference", "reference_bound", "host_lists")
-    tiles = tiles if tiled else 1
+    if not tiled:
+        tx = ty = 1
     lm = {"all": V.LIST_ALL, "bound": V.LIST_BOUND, "reference": V.LIST_REFERENCE, "reference_bound": V.LIST_REFERENCE_BOUND, "host_lists": V.LIST_REFERENCE}[kind]
     nearest, alpha_w = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
     flags = erf | lm | (V.QUANT_NEAREST if nearest else 0) | (V.ALPHA_FROM_W if alpha_w else 0)
@@ -46,16 +57,17 @@ def run_case(pkg, renderer, rng, verbose=False):
         a = int(rng.integers(0, H - 1))
         rows = (a, int(rng.integers(a + 1, H + 1)))
     slice_ = int(rng.choice([0, 0, 8, 16, 64]))
+    bound_k = float(rng.choice([0.0, 6.0, 8.0]))  # 0 selects the default (6)
     q = int(rng.choice([0, 0, 4, 8]))
-    desc = f"{W}x{H} n={n} {kind} tiles={tiles} erf={erf} flags={flags:#x} rows={rows} slice={slice_} q={q}"
+    desc = f"{W}x{H} n={n} {kind} tiles={tx}x{ty} erf={erf} flags={flags:#x} rows={rows} slice={slice_} q={q}"
     if verbose:
         print(desc, flush=True)
     renderer.set_slice(slice_)
     renderer.set_tuning(q, 1)
     try:
         renderer.set_gaussians(scene)
-        f = renderer.frame(cam.view_matrix, origin, W, H, flags, (tiles, tiles), 6.0, rows=rows)
-        lists = reference_lists(scene, cam.view_matrix, tiles) if tiled else None
+        f = renderer.frame(cam.view_matrix, origin, W, H, flags, (tx, ty), bound_k, rows=rows)
+        lists = tile_lists(scene, cam.view_matrix, tx, ty) if tiled else None
         if kind == "host_lists":
             renderer.set_tile_lists(f, [scene[l] for l in lists])
         else:
@@ -76,9 +88,15 @@ def run_case(pkg, renderer, rng, verbose=False):
     if n == 0:
         ref = np.zeros((len(pix), 4), np.float32)
     elif tiled:
-        # W x H frames: oracle_radiance maps pixels to tiles with W // tiles and H // tiles
-        ref = oracle_radiance(scene, cam.view_matrix, origin, W, H, pix, 1 - erf, tiles=tiles, lists=lists, f64="unit" if bounded else False,
-                              near_sigmas=12 if bounded else None)
+        # per reference tile (tx x ty of them, W/tx x H/ty pixels each): the scalar path on that tile's list
+        ref = np.zeros((len(pix), 4), np.float64 if bounded else np.float32)
+        tid = ((pix // np.uint64(W)).astype(np.int64) // (H // ty)) * tx + (pix % np.uint64(W)).astype(np.int64) // (W // tx)
+        for t in np.unique(tid):
+            sel = np.nonzero(tid == t)[0]
+            one = lists[int(t)]
+            if len(one):
+                ref[sel] = oracle_radiance(scene[one], cam.view_matrix, origin, W, H, pix[sel], 1 - erf, f64="unit" if bounded else False,
+                                           near_sigmas=12 if bounded else None)
     else:
         ref = oracle_radiance(scene, cam.view_matrix, origin, W, H, pix, 1 - erf, f64="unit" if bounded else False, near_sigmas=12 if bounded else None)
     got = band.reshape(-1, 4)
