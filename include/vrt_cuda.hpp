@@ -20,6 +20,7 @@
 // here: any VRT_CUDA_E_* from the C ABI, e.g. no GPU -- print a message and terminate the process.
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -207,7 +208,7 @@ cuda_tiles_t cuda_tile_gaussians(const float tw, const float th, const GaussianV
     vrt_cuda_ctx *ctx = cuda::context(device);
     cuda::check(ctx, vrt_cuda_set_gaussians(ctx, reinterpret_cast<const float *>(gaussians.data()), gaussians.size()), "vrt_cuda_set_gaussians");
     // same tile counts as tiles_t: w = ceil(2/tw), h = ceil(2/th)  (types.h:280)
-    const uint64_t w = (uint64_t)(2.f / tw + 0.999f), h = (uint64_t)(2.f / th + 0.999f);
+    const uint64_t w = (uint64_t)std::ceil(2.f / tw), h = (uint64_t)std::ceil(2.f / th);
     return cuda_tiles_t{tw, th, w, h, list_mode, bound_sigmas, device};
 }
 
