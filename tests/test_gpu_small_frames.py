@@ -156,3 +156,52 @@ def test_randomised_small_frames(pkg, renderer):
         _, err = fuzz_frames.run_case(pkg, renderer, rng)
         worst = max(worst, err)
     print(f"worst max-abs radiance error over 120 random frames: {worst:.3e}")
+
+
+def test_k1_hierarchy_full_depth_and_bands(pkg, renderer):
+    """Tile-only: an image large enough for all four cull levels (1024 x 768: 128 x 192 cells), reference tiles that are not
+    square, a row band that cuts through groups of every level.  The band's lists must be exactly the full frame's lists for
+    the cells it renders and empty elsewhere; sampled cells are conservative against the exact per-ray criterion and no
+    longer than the four-plane box (as tests/test_gpu_parity.py checks at 256^2 with a single level pair)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import cpu_lists
+    from oracle_lib import Oracle
+
+    V = pkg.vrt
+    W, H, k = 1024, 768, 6.0
+    scene = pkg.scenes.synthetic(20000, 17, -2.2, -1.5)
+    cam, origin = V.camera_t.app(W, H, rotation=-19.0)
+    renderer.set_gaussians(scene)
+    ncx, ncy = W // 8, H // 4
+    for flags, tiles in (((V.MODE4 & ~V.LIST_MASK) | V.LIST_BOUND, (1, 1)), (bound_flags(V), (32, 24))):
+        f = renderer.frame(cam.view_matrix, origin, W, H, flags, tiles, k)
+        renderer.tile(f)
+        counts, idx = renderer.get_lists()
+        assert len(counts) == ncx * ncy
+        offs = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+        rows = (200, 520) if tiles == (1, 1) else (224, 544)  # 544 = 17 tile rows of 32 px
+        fb = renderer.frame(cam.view_matrix, origin, W, H, flags, tiles, k, rows=rows)
+        renderer.tile(fb)
+        bcounts, bidx = renderer.get_lists()
+        boffs = np.concatenate([[0], np.cumsum(bcounts, dtype=np.int64)])
+        cy = np.arange(ncx * ncy) // ncx
+        inside = (cy * 4 + 4 > rows[0]) & (cy * 4 < rows[1])
+        assert np.array_equal(bcounts[inside], counts[inside]) and not bcounts[~inside].any()
+        first, last = int(np.nonzero(inside)[0][0]), int(np.nonzero(inside)[0][-1])
+        assert np.array_equal(bidx, idx[offs[first] : offs[last + 1]]), "a band's lists differ from the full frame's"
+        assert boffs[-1] == offs[last + 1] - offs[first]
+        if tiles != (1, 1):
+            continue  # the per-ray criterion below is the untiled one
+        rng = np.random.default_rng(8)
+        n_got = n_box = 0
+        for cell in rng.integers(0, ncx * ncy, 40):
+            cx, cyy = int(cell) % ncx, int(cell) // ncx
+            got = set(idx[offs[cell] : offs[cell + 1]].tolist())
+            pix = np.array([(cyy * 4 + r) * W + cx * 8 + c for r in range(4) for c in range(8)], np.uint64)
+            dirs = Oracle.pixel_dirs(cam.view_matrix, origin, W, H, pix)
+            need = set(np.nonzero((cpu_lists.ray_distance_sigmas(scene, origin, dirs) <= k * 0.999).any(1))[0].tolist())
+            planes = cpu_lists.rect_planes(cam.view_matrix, origin, W, H, cx * 8, cx * 8 + 8, cyy * 4, cyy * 4 + 4)
+            box = set(np.nonzero(cpu_lists.rect_bound_member(scene, origin, planes, k * 1.001))[0].tolist())
+            assert need <= got <= box, (cell, sorted(need - got), sorted(got - box))
+            n_got, n_box = n_got + len(got), n_box + len(box)
+        assert n_got <= n_box
