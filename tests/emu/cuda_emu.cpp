@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <map>
+#include <mutex>
 #include <vector>
 
 // ---- fibers: a minimal x86-64 context switch (callee-saved registers + stack pointer) ------------------------------------
@@ -236,6 +237,10 @@ void flush_copies(uint32_t bar)
 }
 } // namespace
 
+static std::recursive_mutex g_api_mutex;
+ApiLock::ApiLock() { g_api_mutex.lock(); }
+ApiLock::~ApiLock() { g_api_mutex.unlock(); }
+
 ThreadCtx &cur() { return g_cur ? g_cur->ctx : g_host_ctx; }
 unsigned lane_id() { return g_cur ? g_cur->lane : 0; }
 unsigned char *dynamic_smem() { return g_block ? g_block->dyn_smem : nullptr; }
@@ -402,12 +407,18 @@ void bulk_copy(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 
 // ---- runtime API ---------------------------------------------------------------------------------------------------------
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "invalid value"); }
+// VRT_EMU_DEVICES pretends to have several GPUs (contexts are independent; the API lock serialises them)
+static int device_count()
+{
+    const char *n = std::getenv("VRT_EMU_DEVICES");
+    return n ? std::max(1, std::min(16, std::atoi(n))) : 1;
+}
 cudaError_t cudaGetDeviceCount(int *n)
 {
-    *n = 1;
+    *n = device_count();
     return cudaSuccess;
 }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaSetDevice(int d) { return d >= 0 && d < device_count() ? cudaSuccess : cudaErrorInvalidValue; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
     std::memset(p, 0, sizeof(*p));

@@ -93,6 +93,12 @@ static inline T unbits(uint64_t u)
     std::memcpy(&v, &u, sizeof(T));
     return v;
 }
+// process-wide recursive lock taken by every C-ABI entry of the translated library (see build_emu.py)
+struct ApiLock
+{
+    ApiLock();
+    ~ApiLock();
+};
 enum { K_BALLOT = 1, K_ANY, K_ALL, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_REDUCE_MAX, K_REDUCE_MIN, K_SYNCWARP };
 } // namespace emu
 

@@ -111,7 +111,7 @@ def test_gpu_parity_tests_under_the_interpreter(build_emu, tma):
     selection = EMU_SELECTION if tma == "lazy" else ["tests/test_gpu_small_frames.py::test_contiguous_lists_through_the_bulk_copy_staging", "tests/test_gpu_parity.py::test_config1_untiled"]
     if tma == "lazy" and os.environ.get("VRT_EMU_FULL") == "1":
         selection = selection + EMU_SLOW
-    env = dict(os.environ, VRT_EMU="1", VRT_EMU_TMA=tma)
+    env = dict(os.environ, VRT_EMU="1", VRT_EMU_TMA=tma, VRT_EMU_DEVICES="3")  # three pretend GPUs for the app's --gpus test
     # (the randomised sweep runs in the AddressSanitizer test below, with fewer cases)
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "--deselect",
                         "tests/test_gpu_small_frames.py::test_randomised_small_frames", *selection], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)

@@ -87,6 +87,33 @@ def test_app_obj_and_synthetic(tmp_path, pkg):
     assert ((img >> 16) & 0xFF).max() > 50  # something was drawn
 
 
+def test_app_multi_gpu_row_bands(tmp_path, pkg):
+    """--gpus N: one host thread and one context per GPU, work-balanced row bands written straight into the host image, one
+    slice size on every GPU.  The composed frame must be the single-GPU picture.  Needs a second device (skipped on a 1-GPU
+    box; the interpreter run of tests/test_emu.py pretends to have three)."""
+    try:
+        pkg.vrt.Renderer(1).close()
+    except pkg.vrt.VrtCudaError:
+        pytest.skip("needs at least two GPUs")
+    n = 3
+    try:
+        pkg.vrt.Renderer(2).close()
+    except pkg.vrt.VrtCudaError:
+        n = 2
+    scene = ["-q", "--synthetic", "3000", "--sigma-range", "-1.8,-1.3", "-w", "128", "--tiles", "8"]
+    out = run_app(scene + ["--gpus", str(n), "-o", "bands.png"], str(tmp_path))
+    assert "3000 Gaussians" in out
+    run_app(scene + ["-o", "one.png"], str(tmp_path))
+    bands, one = read_png(str(tmp_path / "bands.png")), read_png(str(tmp_path / "one.png"))
+    assert ((bands >> 16) & 0xFF).max() > 50
+    assert channel_diff_lsb(bands, one) <= 1  # (the pinned slice / emitter block may group the fp32 sums differently)
+    # an orbit of three frames re-balances the bands every frame
+    run_app(scene + ["--gpus", str(n), "--frames", "3", "-r", "60", "-o", "turn.png"], str(tmp_path))
+    run_app(scene + ["--frames", "3", "-r", "60", "-o", "ref.png"], str(tmp_path))
+    for k in (1, 2, 3):
+        assert channel_diff_lsb(read_png(str(tmp_path / f"turn_{k}.png")), read_png(str(tmp_path / f"ref_{k}.png"))) <= 1, k
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_check")), reason="oracle/_ref/dropin_check not built")
 def test_dropin_with_reference_types():
     """oracle/dropin_check.cpp: the reference's own camera_t / gaussians_t / tiles_t objects passed to vrt::cuda_* entries,
