@@ -148,3 +148,69 @@ def test_kernels_under_address_sanitizer(build_emu):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_frames.py"), "--emu", "--cases", cases, "--seed", "3"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and "fuzz ok" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def _rank_worker(rank, world, port, lib_path, result_path):
+    """One rank of bench.py's multi-GPU protocol with the emulated library standing in for the rank's GPU and gloo for NCCL."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    lib = ctypes.CDLL(lib_path)
+    for sym, (res, args) in pkg._ffi.CUDA_SYMBOLS.items():
+        fn = getattr(lib, sym)
+        fn.restype, fn.argtypes = res, args
+    pkg._ffi._cuda = lib
+    from vrt_b200 import bands as B
+
+    V = pkg.vrt
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W, tiles = 96, 12
+    # rank 0 owns the scene; everyone receives it (bench.py: dist.broadcast of the device copy)
+    scene = torch.from_numpy(pkg.scenes.synthetic(1500, 5, -1.6, -1.2)) if rank == 0 else torch.zeros((1500, 10), dtype=torch.float32)
+    dist.broadcast(scene, 0)
+    r = V.Renderer(0)
+    r.set_gaussians(scene.numpy())
+    cam, origin = V.camera_t.app(W, W, rotation=9.0)
+    flags = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+    full = r.frame(cam.view_matrix, origin, W, W, flags, (tiles, tiles), 6.0)
+    r.tile(full)
+    row_cost, row_px = r.row_costs()
+    bounds = B.split_rows(row_cost, row_px, world, W, align=W // tiles)
+    r.set_slice(r.auto_slice(1.0 / world))
+    band = r.frame(cam.view_matrix, origin, W, W, flags, (tiles, tiles), 6.0, rows=(bounds[rank], bounds[rank + 1]))
+    image = np.zeros((W, W), np.uint32)
+    r.tile(band)
+    _, _, st = r.render(band, True, False, image=image)
+    t = torch.from_numpy(image.view(np.int32))
+    B.gather_bands(t, bounds, rank, world, dist)
+    terms = torch.tensor([st["terms_listed"]], dtype=torch.float64)
+    dist.all_reduce(terms)
+    if rank == 0:
+        whole, _, st_full = r.frame_render(full, True, False)
+        with open(result_path, "w") as f:
+            f.write(f"{int(np.array_equal(whole, image))} {int(terms.item() == st_full['terms_listed'])} {int(whole.any())} {' '.join(map(str, bounds))}")
+    dist.barrier()
+    dist.destroy_process_group()
+    r.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_protocol_with_rendering(build_emu, world, tmp_path):
+    """bench.py's N > 1 protocol end to end on the CPU: scene broadcast, full-frame tiling for the row costs, cost-balanced
+    bands on tile rows, one slice size for every rank, every rank renders its band with the real kernels (interpreter), bands
+    gathered to rank 0 (gloo in place of NCCL) -- and the gathered image must equal the frame one context renders alone, bit
+    for bit, with the listed work of the bands adding up to the frame's."""
+    import torch.multiprocessing as mp
+    from test_bands import _free_port
+
+    result = str(tmp_path / "res.txt")
+    mp.spawn(_rank_worker, args=(world, _free_port(), build_emu.build(), result), nprocs=world, join=True)
+    equal, terms_add_up, drawn, *bounds = open(result).read().split()
+    assert (equal, terms_add_up, drawn) == ("1", "1", "1"), (equal, terms_add_up, drawn, bounds)
+    assert len(bounds) == world + 1 and bounds[0] == "0" and bounds[-1] == "96"
