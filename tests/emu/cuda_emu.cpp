@@ -93,7 +93,6 @@ constexpr size_t GUARD = 256;
 #endif
 constexpr unsigned char GUARD_BYTE = 0xE7, FRESH_BYTE = 0xA5;
 std::map<void *, size_t> g_allocs;
-char g_last_error[256] = "";
 
 void yield_to_scheduler() { emu_switch(&g_cur->sp, g_sched_sp); }
 
