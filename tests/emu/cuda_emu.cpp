@@ -84,6 +84,10 @@ struct PendingCopy
 };
 std::vector<PendingCopy> g_pending;
 bool g_tma_lazy = true;
+// VRT_EMU_ORDER=reverse runs the threads of a CTA (and the lanes of a warp) from the highest index down.  After a collective
+// the last lane to arrive runs on first (lane 31 forward, lane 0 reversed), so code that only works for one order -- shared
+// memory handed between lanes without a __syncwarp -- reads stale data in the other; the tests run both
+bool g_reverse = false;
 
 // guarded allocations: [guard | payload | guard]
 #ifdef __SANITIZE_ADDRESS__
@@ -173,8 +177,9 @@ void run_block(Block &b)
     {
         bool progress = false;
         unsigned remaining = 0;
-        for (Fiber &f : b.fibers)
+        for (size_t i = 0; i < b.fibers.size(); ++i)
         {
+            Fiber &f = b.fibers[g_reverse ? b.fibers.size() - 1 - i : i];
             if (f.done) continue;
             remaining++;
             if (!runnable(f)) continue;
@@ -210,7 +215,7 @@ void wait_in_warp(Fiber &f)
     Fiber *first = &g_block->fibers[(size_t)(&f - g_block->fibers.data()) & ~(size_t)31];
     for (unsigned k = 1; k < 32; ++k)
     {
-        Fiber &n = first[(f.lane + k) & 31];
+        Fiber &n = first[(g_reverse ? f.lane + 32 - k : f.lane + k) & 31];
         if (runnable(n))
         {
             g_cur = &n;
@@ -311,6 +316,8 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *ar
     if ((uint64_t)grid.x * grid.y * grid.z == 0) fatal("empty grid"); // cudaErrorInvalidConfiguration on the GPU
     static const char *lazy = std::getenv("VRT_EMU_TMA");
     g_tma_lazy = !(lazy && std::strcmp(lazy, "eager") == 0);
+    static const char *order = std::getenv("VRT_EMU_ORDER");
+    g_reverse = order && std::strcmp(order, "reverse") == 0;
     std::vector<unsigned char> dyn(smem + 128);
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)

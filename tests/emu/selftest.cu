@@ -1,7 +1,7 @@
 // selftest.cu -- TEST INFRASTRUCTURE ONLY: kernels that pin the SIMT interpreter of cuda_emu.h itself (tests/test_emu.py).
 // Case 0 checks the collectives, the CTA barrier, atomics and the bulk-copy / mbarrier model against known answers;
 // cases 1-4 each contain a deliberate bug the interpreter must abort on (out-of-bounds write, divergent collectives,
-// deadlock, a bulk copy nobody waits for).
+// deadlock, a bulk copy nobody waits for); case 5 is a missing __syncwarp that only the reversed lane order exposes.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -122,6 +122,18 @@ __global__ void k_unwaited_copy(const float4 *src)
     }
 }
 
+// a hand-off between lanes through shared memory WITHOUT the __syncwarp it needs: correct only if lane 0 happens to run first
+// after the collective (the interpreter continues with the LAST lane to arrive: lane 31 forward, lane 0 reversed)
+__global__ void k_missing_syncwarp(uint32_t *out)
+{
+    __shared__ uint32_t s;
+    const int lane = threadIdx.x;
+    if (lane == 0) s = 0;
+    __syncwarp();
+    if (lane == 0) s = 42;
+    out[lane] = s; // BUG (deliberate): no __syncwarp() between the write and the reads
+}
+
 #define REQUIRE(cond)                                                        \
     do                                                                       \
     {                                                                        \
@@ -181,6 +193,17 @@ extern "C" int emu_selftest(int which)
     }
     uint32_t *buf = nullptr;
     cudaMalloc((void **)&buf, sizeof(uint32_t) * 1024);
+    if (which == 5)
+    {
+        // returns how many lanes saw the value: 32 when lane 0 runs first, fewer in the other lane order
+        k_missing_syncwarp<<<1, 32>>>(buf);
+        uint32_t h[32];
+        cudaMemcpyAsync(h, buf, sizeof(h), cudaMemcpyDeviceToHost, nullptr);
+        int seen = 0;
+        for (uint32_t v : h) seen += v == 42u;
+        cudaFree(buf);
+        return seen;
+    }
     if (which == 1) k_oob<<<1, 32>>>(buf, 1024);
     if (which == 2) k_divergent<<<1, 32>>>((int *)buf);
     if (which == 3) k_deadlock<<<1, 64>>>();

@@ -78,6 +78,14 @@ def test_interpreter_selftest(build_emu):
     for case, message in expect.items():
         r = subprocess.run([sys.executable, "-c", f"import ctypes; ctypes.CDLL({lib!r}).emu_selftest({case})"], capture_output=True, text=True, timeout=120)
         assert r.returncode != 0 and message in r.stderr, (case, r.returncode, r.stderr[-500:])
+    # a missing __syncwarp is invisible in one lane order and shows in the other (after a collective the last lane to arrive runs
+    # on first: lane 31 in the forward order, lane 0 in the reversed one), so every selection is run in both orders
+    seen = {}
+    for order in ("forward", "reverse"):
+        r = subprocess.run([sys.executable, "-c", f"import ctypes, sys; sys.exit(ctypes.CDLL({lib!r}).emu_selftest(5))"], env=dict(os.environ, VRT_EMU_ORDER=order),
+                           capture_output=True, text=True, timeout=120)
+        seen[order] = r.returncode
+    assert max(seen.values()) == 32 and min(seen.values()) < 32, seen
 
 
 def test_translation_covers_every_cuda_construct(build_emu):
@@ -112,6 +120,12 @@ def test_gpu_parity_tests_under_the_interpreter(build_emu, tma):
     if tma == "lazy" and os.environ.get("VRT_EMU_FULL") == "1":
         selection = selection + EMU_SLOW
     env = dict(os.environ, VRT_EMU="1", VRT_EMU_TMA=tma, VRT_EMU_DEVICES="3")  # three pretend GPUs for the app's --gpus test
+    if tma == "eager":
+        # the second leg also runs the lanes of every warp from 31 down to 0: shared memory handed from one lane to another
+        # without a __syncwarp (or a copy waited for before lane 0 issued it) only works in the forward order
+        env["VRT_EMU_ORDER"] = "reverse"
+        selection = selection + ["tests/test_gpu_small_frames.py::test_depth_window_small", "tests/test_gpu_small_frames.py::test_split_cells_and_bands_small",
+                                 "tests/test_gpu_parity.py::test_row_bands_compose", "tests/test_gpu_approx.py::test_variants_on_device_built_lists"]
     # (the randomised sweep runs in the AddressSanitizer test below, with fewer cases)
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "--deselect",
                         "tests/test_gpu_small_frames.py::test_randomised_small_frames", *selection], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
