@@ -88,6 +88,7 @@ bool g_tma_lazy = true;
 // the last lane to arrive runs on first (lane 31 forward, lane 0 reversed), so code that only works for one order -- shared
 // memory handed between lanes without a __syncwarp -- reads stale data in the other; the tests run both
 bool g_reverse = false;
+uint32_t g_random = 0; // xorshift state, 0 = off
 
 // guarded allocations: [guard | payload | guard]
 #ifdef __SANITIZE_ADDRESS__
@@ -213,9 +214,19 @@ void run_block(Block &b)
 void wait_in_warp(Fiber &f)
 {
     Fiber *first = &g_block->fibers[(size_t)(&f - g_block->fibers.data()) & ~(size_t)31];
+    // VRT_EMU_ORDER=random:<seed>: the search for the next lane starts at a pseudo-random lane (xorshift), so lanes interleave
+    // differently at every collective
+    unsigned jump = 0;
+    if (g_random)
+    {
+        g_random ^= g_random << 13;
+        g_random ^= g_random >> 17;
+        g_random ^= g_random << 5;
+        jump = g_random & 31u;
+    }
     for (unsigned k = 1; k < 32; ++k)
     {
-        Fiber &n = first[(g_reverse ? f.lane + 32 - k : f.lane + k) & 31];
+        Fiber &n = first[(g_reverse ? f.lane + 32 - k : f.lane + k + jump) & 31];
         if (runnable(n))
         {
             g_cur = &n;
@@ -318,6 +329,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*body)(void *), void *ar
     g_tma_lazy = !(lazy && std::strcmp(lazy, "eager") == 0);
     static const char *order = std::getenv("VRT_EMU_ORDER");
     g_reverse = order && std::strcmp(order, "reverse") == 0;
+    if (order && std::strncmp(order, "random:", 7) == 0 && g_random == 0) g_random = (uint32_t)std::atoi(order + 7) * 2654435761u + 1u;
     std::vector<unsigned char> dyn(smem + 128);
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
