@@ -262,6 +262,9 @@ def test_bench_cuda_arm_contract(build_emu, extra):
     assert roof["bound"] == "fp32" and roof["kernel"] == "k2_render" and roof["unit"] == "TFLOP/s" and roof["flops_per_term"] == 15.0
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) <= 1e-9
     assert abs(roof["achieved"] - roof["terms_per_launch"] * 15.0 / (roof["ms_per_launch"] * 1e-3) / 1e12) <= 1e-6 * roof["achieved"]
+    pm = roof["pipe_model"]
+    assert pm["ceiling_terms_per_s"] == 2 * 4 * 32 / 8.0 * 1965e6 and 0 < pm["frac_of_ceiling"] < 1  # 2 pretend SMs at the B200's max clock
+    assert abs(pm["frac_of_ceiling"] / roof["frac"] - roof["peak"] * 1e12 / 15.0 / pm["ceiling_terms_per_s"]) <= 1e-9
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     if extra:
         assert "cpu_baseline" not in d and cfg["slice"] == 16 and cfg["depth_window_mode"] is None and "literal" in cfg["lists"]
