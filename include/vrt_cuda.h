@@ -9,9 +9,10 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
  * VRT_CUDA_E_* code on failure (vrt_cuda_last_error() gives the text); nothing throws, exits or
  * falls back to a CPU implementation -- without a CUDA device vrt_cuda_create() fails.
- * One context drives one GPU and owns one stream; contexts on different GPUs are independent (one per rank, or one
- * host thread each as in the app's --gpus mode).  The frame geometry lives in the device's constant memory, so two
- * contexts on the SAME GPU must not have frames in flight at the same time (tile + render of one, then the other).
+ * One context drives one GPU and owns one stream; contexts are independent of each other, also on the SAME GPU: a frame's
+ * geometry travels in the kernels' parameter blocks and the lists live in the context's own buffers, so two contexts can
+ * have frames in flight on one device at the same time (the reference's entries are re-entrant, rt.h:259, 293).
+ * A single context is driven by one host thread at a time; vrt_cuda_abort may be called from any thread.
  * Limits: images up to 65536 x 65536 with at most 2^22 8x4-pixel cells (about 134 Mpixel) per frame, reference tiles
  * per axis <= 1024, fewer than 2^31 Gaussians (device indices are 32-bit).
  */
@@ -24,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VRT_CUDA_ABI_VERSION 4
+#define VRT_CUDA_ABI_VERSION 5
 
 /* Error codes */
 #define VRT_CUDA_OK 0
@@ -32,6 +33,7 @@ extern "C" {
 #define VRT_CUDA_E_CUDA (-2)     /* CUDA runtime error (text in last_error)      */
 #define VRT_CUDA_E_STATE (-3)    /* call order: no Gaussians / no lists yet      */
 #define VRT_CUDA_E_NOMEM (-4)
+#define VRT_CUDA_INTERRUPTED 1   /* not an error: `running` went false mid-frame (the `true` of rt.h:244-246, 308-309) */
 
 /* ---- frame flags ---------------------------------------------------------------------------- */
 /* erf variant.  AS = Abramowitz-Stegun 7.1.27 with the reference's coefficients
@@ -71,12 +73,23 @@ extern "C" {
  * vrt_cuda_get_lists and the membership they report stay literal.  NO_SKIP (given to the tile call AND the render call)
  * keeps every entry and evaluates every listed term: terms_executed == terms_listed. */
 #define VRT_CUDA_NO_SKIP (1u << 6)
-/* Depth-window mode (bounded per-cell lists only): K1 sorts every cell's list by depth along the cell's centre ray and K2
- * resolves an occluder that lies >= t_sat standard widths in front of (behind) every sample of the current emitter block,
- * for every pixel of the cell, as the constant +A (-A) it evaluates to -- erf is saturated to +-1 in fp32 there -- instead
- * of 5Q full terms.  Same image (sums are reordered: differences ~1e-7), several times fewer evaluated terms;
- * vrt_cuda_stats.terms_saturated counts the terms resolved that way. */
+/* Banded evaluation -- the DEFAULT wherever K2 walks depth-sorted per-cell lists (every *_BOUND mode and the visible lists of
+ * the literal modes).  K1 sorts every cell's list by depth along the cell's centre ray; an occluder that lies >= t_sat
+ * standard widths in front of (behind) every sample of an emitter pair, for every pixel of the cell, is resolved as the
+ * constant +A (-A) it evaluates to -- erf is saturated to +-1 in fp32 there -- and only the band of occluders around the
+ * pair's own depth is evaluated term by term.  Same image (sums are reordered: differences ~1e-6), several times fewer
+ * evaluated terms; vrt_cuda_stats.terms_saturated counts the terms resolved that way.  DEPTH_WINDOW is the round-1 name of
+ * the opt-in and is still accepted (it now only asserts that the lists can take the banded kernel). */
 #define VRT_CUDA_DEPTH_WINDOW (1u << 7)
+/* Evaluate every listed term (the round-1 default): no saturation shortcut, no early exit.  terms_executed then counts
+ * every (pixel, sample, occluder) triple the lists name, minus the warp-uniform zero-weight skips. */
+#define VRT_CUDA_EVAL_ALL (1u << 12)
+/* Transmittance early exit (banded kernel).  ln T(s) is non-increasing in s (every weight A_j >= 0, erf increasing), so once
+ * T at a sample no remaining emitter's samples precede is below eps / (remaining emission weight) for every pixel of the
+ * cell, the emitters behind change no channel by more than eps = 1e-6 and the cell stops (a warp-uniform break; replaces the
+ * unconditional emitter loop rt.h:209-221).  vrt_cuda_stats.terms_terminated counts the terms dropped.  Disabled
+ * automatically when the scene holds a negative magnitude or a non-positive sigma; NO_TERMINATE disables it explicitly. */
+#define VRT_CUDA_NO_TERMINATE (1u << 13)
 
 /* The reference's alternative approximations as selectable device functions (src/vrt/approx.h:10-46; the template
  * arguments <Exp, Erf> of the render entries, src/vrt/rt.h:315, 344, exercised by tests/img-error.cpp:40-43).
@@ -138,7 +151,8 @@ typedef struct vrt_cuda_stats
     float ms_render;          /* device time of the render kernel(s)                                      */
     float ms_total;           /* first kernel to last kernel / copy of the call                           */
     uint32_t slice;           /* emitters per work item of split cells used by this frame (see vrt_cuda_set_slice)  */
-    double terms_saturated;   /* depth-window mode: terms resolved by the saturation shortcut (not in terms_executed) */
+    double terms_saturated;   /* banded evaluation: terms resolved by the saturation shortcut (not in terms_executed) */
+    double terms_terminated;  /* banded evaluation: terms dropped by the transmittance early exit                    */
 } vrt_cuda_stats;
 
 typedef struct vrt_cuda_ctx vrt_cuda_ctx;
@@ -189,6 +203,28 @@ int vrt_cuda_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *im
  * vrt_cuda_sync() waits for it.  Used by the multi-GPU path (bands are gathered with NCCL afterwards). */
 int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image_dev, float *radiance_dev,
                            vrt_cuda_stats *stats);
+
+/* The `const bool &running` argument of the reference's entries (rt.h:228, 252, 316, 346): `running` points at the caller's
+ * flag (one byte, C++ bool), which another thread may clear while the frame renders (main.cpp:244: the viewer thread).  The
+ * reference polls it per pixel / per tile (rt.h:244-246, 289, 334, 382) and returns true; here the host polls it while the
+ * frame is in flight and raises a word in device memory the persistent render warps check before every work item.  Returns
+ * VRT_CUDA_INTERRUPTED (the image is then partial and not copied back), 0 when the frame completed, < 0 on error. */
+int vrt_cuda_render_interruptible(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance,
+                                  vrt_cuda_stats *stats, const volatile unsigned char *running);
+/* Raise (1) / clear (0) the abort word directly, from any thread: a vrt_cuda_render / vrt_cuda_render_device in flight on
+ * this context stops taking work items.  The caller clears it before the next frame. */
+int vrt_cuda_abort(vrt_cuda_ctx *ctx, int on);
+
+/* Caller buffers.  The reference's callers hand in plain (pageable) memory -- `image` is simd::aligned_malloc'd once and
+ * reused every frame (main.cpp:245, 338) -- which CUDA copies through a staging buffer at a fraction of the PCIe rate.
+ * With pinning on, vrt_cuda_set_gaussians and vrt_cuda_render page-lock the buffer they are given (cudaHostRegister, once
+ * per pointer; up to four registrations are kept) and copy at full rate.  OPT-IN, because the caller must keep such a
+ * buffer alive until it turns pinning off again (which releases every registration) or destroys the context. */
+int vrt_cuda_set_host_pinning(vrt_cuda_ctx *ctx, int on);
+/* Explicit form: page-lock [p, p + bytes) (rounded out to pages) for every device of the process until vrt_cuda_unpin_buffer(p);
+ * what an application that owns its image buffer for its whole run calls once (the host app does). */
+int vrt_cuda_pin_buffer(vrt_cuda_ctx *ctx, void *p, uint64_t bytes);
+int vrt_cuda_unpin_buffer(vrt_cuda_ctx *ctx, void *p);
 
 /* vrt_cuda_tile + vrt_cuda_render in one call: one iteration of the app's frame loop (main.cpp:257-297). */
 int vrt_cuda_frame_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance,

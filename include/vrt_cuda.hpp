@@ -59,9 +59,14 @@ namespace cuda
         return h.ctx[device];
     }
 
+    /// Opt in to page-locking the buffers handed to the render entries (`image`, the Gaussian vector): the reference's main
+    /// allocates `image` once with simd::aligned_malloc and reuses it every frame (main.cpp:245, 338), so one registration
+    /// makes every frame's copy-back run at PCIe rate.  The buffers must stay allocated until pin_host_buffers(false).
+    inline void pin_host_buffers(bool on, int device = 0) { vrt_cuda_set_host_pinning(context(device), on ? 1 : 0); }
+
     inline void check(vrt_cuda_ctx *ctx, int rc, const char *what)
     {
-        if (rc == VRT_CUDA_OK) return;
+        if (rc == VRT_CUDA_OK || rc == VRT_CUDA_INTERRUPTED) return;
         std::fprintf(stderr, "[ ERROR ]\tvrt::cuda: %s failed (%d): %s\n", what, rc, vrt_cuda_last_error(ctx));
         std::exit(EXIT_FAILURE);
     }
@@ -82,6 +87,19 @@ namespace cuda
         return f;
     }
 
+    /// Tile (optionally) + render while watching the caller's `running` flag: the reference polls it per pixel / per tile
+    /// (rt.h:244-246, 289, 334, 382) and returns true when it went false; here the C ABI polls it while the frame is in
+    /// flight and stops the persistent render warps (vrt_cuda_render_interruptible).
+    inline bool render_running(vrt_cuda_ctx *ctx, const vrt_cuda_frame &f, uint32_t *image, vrt_cuda_stats *stats, const bool &running, bool tile)
+    {
+        static_assert(sizeof(bool) == 1, "the C ABI reads `running` as one byte");
+        if (tile) check(ctx, vrt_cuda_tile(ctx, &f), "vrt_cuda_tile");
+        if (!running) return true;
+        const int rc = vrt_cuda_render_interruptible(ctx, &f, image, nullptr, stats, reinterpret_cast<const volatile unsigned char *>(&running));
+        check(ctx, rc, "vrt_cuda_render_interruptible");
+        return rc == VRT_CUDA_INTERRUPTED || !running;
+    }
+
     /// Untiled entries: every Gaussian for every pixel (or the bounded lists if `flags` says so).
     template <class Camera, class Vec4, class Gaussians>
     bool render_gaussians(uint32_t width, uint32_t height, uint32_t *image, const Camera &cam, const Vec4 &origin,
@@ -92,8 +110,7 @@ namespace cuda
         vrt_cuda_ctx *ctx = context(device);
         const vrt_cuda_frame f = make_frame(width, height, cam, origin, flags);
         check(ctx, vrt_cuda_set_gaussians(ctx, reinterpret_cast<const float *>(gaussians.gaussians.data()), gaussians.gaussians.size()), "vrt_cuda_set_gaussians");
-        check(ctx, vrt_cuda_frame_render(ctx, &f, image, nullptr, stats), "vrt_cuda_frame_render");
-        return !running;
+        return render_running(ctx, f, image, stats, running, true);
     }
 
     /// Tiled entries: the caller's tiles_t supplies one list per reference tile (row-major, y outer).
@@ -115,8 +132,7 @@ namespace cuda
             if (!list.empty()) std::memcpy(concat.data() + offsets[t] * 10, reinterpret_cast<const float *>(list.data()), list.size() * 40);
         }
         check(ctx, vrt_cuda_set_tile_lists(ctx, &f, concat.data(), offsets.data(), n_tiles), "vrt_cuda_set_tile_lists");
-        check(ctx, vrt_cuda_render(ctx, &f, image, nullptr, stats), "vrt_cuda_render");
-        return !running;
+        return render_running(ctx, f, image, stats, running, false);
     }
 } // namespace cuda
 
@@ -222,7 +238,6 @@ bool cuda_render_frame(const uint32_t width, const uint32_t height, uint32_t *im
     vrt_cuda_ctx *ctx = cuda::context(tiles.device);
     const uint32_t flags = (mode_flags & ~VRT_CUDA_LIST_MASK) | tiles.list_mode;
     const vrt_cuda_frame f = cuda::make_frame(width, height, cam, origin, flags, (uint32_t)tiles.w, (uint32_t)tiles.h, tiles.bound_sigmas);
-    cuda::check(ctx, vrt_cuda_frame_render(ctx, &f, image, nullptr, stats), "vrt_cuda_frame_render");
-    return !running;
+    return cuda::render_running(ctx, f, image, stats, running, true);
 }
 } // namespace vrt

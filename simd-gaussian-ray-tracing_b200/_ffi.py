@@ -47,6 +47,7 @@ class Stats(ctypes.Structure):
         ("ms_total", c_f),
         ("slice", c_u32),
         ("terms_saturated", c_d),
+        ("terms_terminated", c_d),
     ]
 
     def as_dict(self):
@@ -67,6 +68,11 @@ CUDA_SYMBOLS = {
     "vrt_cuda_render": (c_i, [vp, ctypes.POINTER(Frame), vp, vp, ctypes.POINTER(Stats)]),
     "vrt_cuda_render_device": (c_i, [vp, ctypes.POINTER(Frame), vp, vp, ctypes.POINTER(Stats)]),
     "vrt_cuda_frame_render": (c_i, [vp, ctypes.POINTER(Frame), vp, vp, ctypes.POINTER(Stats)]),
+    "vrt_cuda_render_interruptible": (c_i, [vp, ctypes.POINTER(Frame), vp, vp, ctypes.POINTER(Stats), vp]),
+    "vrt_cuda_abort": (c_i, [vp, c_i]),
+    "vrt_cuda_set_host_pinning": (c_i, [vp, c_i]),
+    "vrt_cuda_pin_buffer": (c_i, [vp, vp, c_u64]),
+    "vrt_cuda_unpin_buffer": (c_i, [vp, vp]),
     "vrt_cuda_row_costs": (c_i, [vp, vp, c_u32, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32)]),
     "vrt_cuda_set_tuning": (c_i, [vp, c_i, c_i]),
     "vrt_cuda_fp32_peak": (c_i, [vp, c_i, ctypes.POINTER(c_d)]),

@@ -1,13 +1,16 @@
 // k1_tile.cuh -- K0 (per-Gaussian frame records) and K1 (multi-level culling, scans, depth sort, cost histogram, work queue).
-// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace (one translation unit, so
-// every kernel sees the same __constant__ frame geometry).  Not a stand-alone header.
+// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace.  Not a stand-alone header.
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
 // K0: per-Gaussian frame constants
 // ------------------------------------------------------------------------------------------------
 // cull record, 32 B: (oc.xyz, sigma) and (mu'.x, mu'.y, 3.3 sigma', valid) of the reference's tiling projection (rt.cpp:35-45)
-__global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__restrict__ rec, float4 *__restrict__ cullrec)
+// scene_info[0] = max |albedo component| as float bits (all non-negative, so the unsigned order is the float order),
+// scene_info[1] = 1 when some magnitude is negative or some sigma is not positive: T(s) is then not monotone and K2 must not
+// terminate early.
+__global__ void k0_prepare(const FrameGeom G, const float *__restrict__ aos, uint64_t n, Rec *__restrict__ rec, float4 *__restrict__ cullrec,
+                           uint32_t *__restrict__ scene_info)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -16,7 +19,7 @@ __global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__res
     const float mx = g[4], my = g[5], mz = g[6], mw = g[7];
     const float sigma = g[8], mag = g[9];
     Rec r;
-    r.a = make_float4(mx - c_geom.origin[0], my - c_geom.origin[1], mz - c_geom.origin[2], mw * mw);
+    r.a = make_float4(mx - G.origin[0], my - G.origin[1], mz - G.origin[2], mw * mw);
     const float rr = 1.f / (1.41421356237309504880f * sigma);
     r.b = make_float4(rr, LOG2E / (2.f * sigma * sigma), sigma * mag * SQRT_PI_2 * LOG2E, sigma);
     r.c = make_float4(ax, ay, az, aw);
@@ -24,7 +27,7 @@ __global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__res
     if (cullrec != nullptr)
     {
         // proj = view * (mu.xyz, 1), GLM operand order (c0 x + c1 y) + (c2 z + c3 w)
-        const float *v = c_geom.view;
+        const float *v = G.view;
         const float px = (v[0] * mx + v[4] * my) + (v[8] * mz + v[12]);
         const float py = (v[1] * mx + v[5] * my) + (v[9] * mz + v[13]);
         const float pz = (v[2] * mx + v[6] * my) + (v[10] * mz + v[14]);
@@ -34,6 +37,15 @@ __global__ void k0_prepare(const float *__restrict__ aos, uint64_t n, Rec *__res
         // one 32-byte sector per Gaussian holds everything K1 tests: (oc.xyz, sigma) and the reference projection
         cullrec[2 * i] = make_float4(r.a.x, r.a.y, r.a.z, sigma);
         cullrec[2 * i + 1] = make_float4(px * inv, py * inv, REF_CULL_SIGMAS * sg, valid ? 1.f : 0.f);
+    }
+    if (scene_info != nullptr)
+    {
+        // the running maximum is read first: after the first few Gaussians almost no thread issues an atomic
+        float am = fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fmaxf(fabsf(az), fabsf(aw)));
+        am = (am == am) ? am : 3.0e38f;
+        const uint32_t bits = __float_as_uint(am);
+        if (bits > scene_info[0]) atomicMax(&scene_info[0], bits);
+        if ((mag < 0.f || !(sigma > 0.f)) && scene_info[1] == 0u) atomicOr(&scene_info[1], 1u);
     }
 }
 
@@ -64,9 +76,8 @@ __device__ __forceinline__ void orient_normalize(float *n, const float *towards,
 }
 
 // pixel rect [x0,x1) x [y0,y1) -> frustum planes through the extreme sample positions
-__device__ __forceinline__ void make_rect(int x0, int x1, int y0, int y1, CullRect &rc)
+__device__ __forceinline__ void make_rect(const FrameGeom &G, int x0, int x1, int y0, int y1, CullRect &rc)
 {
-    const FrameGeom &G = c_geom;
     rc.u0 = -1.f + (float)x0 / G.half_w; rc.u1 = -1.f + (float)(x1 - 1) / G.half_w;
     rc.v0 = -1.f + (float)y0 / G.half_h; rc.v1 = -1.f + (float)(y1 - 1) / G.half_h;
     float Wv[3], a[3];
@@ -98,9 +109,8 @@ __device__ __forceinline__ bool ref_axis(float c, float mu, float half_t, float 
 // between their normals) is nearest to the corner ray only if it projects beyond the edge on BOTH faces (su - sv c > 0 and
 // sv - su c > 0) -- then its distance to that ray's line decides (rounded corners instead of a box: ~14 % shorter lists);
 // otherwise a face is nearest and its plane distance (already <= lim) is the true distance.
-__device__ __forceinline__ bool near_frustum(const CullRect &rc, const float *p, float dl, float dr, float db, float dt, float sgn, float lim)
+__device__ __forceinline__ bool near_frustum(const FrameGeom &G, const CullRect &rc, const float *p, float dl, float dr, float db, float dt, float sgn, float lim)
 {
-    const FrameGeom &G = c_geom;
     const float sl = sgn * dl, sr = sgn * dr, sb = sgn * db, st = sgn * dt;
     const float su = fmaxf(sl, sr), sv = fmaxf(sb, st);
     if (!(su <= lim && sv <= lim)) return false;
@@ -117,24 +127,23 @@ __device__ __forceinline__ bool near_frustum(const CullRect &rc, const float *p,
     return px * px + py * py + pz * pz <= lim * lim;
 }
 
-__device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, const float sigma, const float4 cr)
+__device__ __forceinline__ bool cull_test(const FrameGeom &G, const CullRect &rc, const float4 a, const float sigma, const float4 cr)
 {
-    const FrameGeom &G = c_geom;
     if (G.use_ref)
     {
         if (cr.w == 0.f) return false;
         const float hx = G.tw / 2, hy = G.th / 2;
         if (rc.exact_tile)
         {
-            if (!(ref_axis(c_tile_cx[rc.tx0], cr.x, hx, cr.z) && ref_axis(c_tile_cy[rc.ty0], cr.y, hy, cr.z))) return false;
+            if (!(ref_axis(G.tile_cx[rc.tx0], cr.x, hx, cr.z) && ref_axis(G.tile_cy[rc.ty0], cr.y, hy, cr.z))) return false;
         }
         else
         {
             // |c - mu| - |c| is monotone in c, so a tile range passes iff one of its end tiles does;
             // the slack keeps the coarse level conservative against rounding of the exact test.
             const float s = cr.z + 1e-4f;
-            const bool px = ref_axis(c_tile_cx[rc.tx0], cr.x, hx, s) || ref_axis(c_tile_cx[rc.tx1], cr.x, hx, s);
-            const bool py = ref_axis(c_tile_cy[rc.ty0], cr.y, hy, s) || ref_axis(c_tile_cy[rc.ty1], cr.y, hy, s);
+            const bool px = ref_axis(G.tile_cx[rc.tx0], cr.x, hx, s) || ref_axis(G.tile_cx[rc.tx1], cr.x, hx, s);
+            const bool py = ref_axis(G.tile_cy[rc.ty0], cr.y, hy, s) || ref_axis(G.tile_cy[rc.ty1], cr.y, hy, s);
             if (!(px && py)) return false;
         }
     }
@@ -146,7 +155,7 @@ __device__ __forceinline__ bool cull_test(const CullRect &rc, const float4 a, co
         const float dl = dot3(p, rc.nl), dr = dot3(p, rc.nr), db = dot3(p, rc.nb), dt = dot3(p, rc.nt);
         // the reference integrates along the whole line (samples with s < 0 are not guarded, rt.h:155-160),
         // so the mirrored frustum counts too
-        if (!(near_frustum(rc, p, dl, dr, db, dt, 1.f, lim) || near_frustum(rc, p, dl, dr, db, dt, -1.f, lim))) return false;
+        if (!(near_frustum(G, rc, p, dl, dr, db, dt, 1.f, lim) || near_frustum(G, rc, p, dl, dr, db, dt, -1.f, lim))) return false;
     }
     return true;
 }
@@ -166,7 +175,7 @@ struct CullLevel
 // 32 candidates per step, one per lane: predicate -> ballot -> popc of the lower lanes = ordered slot (lists keep
 // ascending Gaussian index, so K2's sums are reproducible).
 template <bool WRITE>
-__global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root, const CullLevel L,
+__global__ void __launch_bounds__(256) k1_cull(const FrameGeom G, const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root, const CullLevel L,
                                                const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ parent_idx,
                                                uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, uint32_t *__restrict__ out_idx,
                                                uint32_t n_work)
@@ -174,7 +183,6 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= n_work) return;
-    const FrameGeom &G = c_geom;
     const uint32_t group = wid / L.n_seg, seg = wid % L.n_seg;
     const int gxi = group % L.ngx, gyi = group / L.ngx;
     // pixel rect of the group = union of its cells' rects
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
     if (in_band && end > begin)
     {
         CullRect rc;
-        make_rect(x0, x1, y0, y1, rc);
+        make_rect(G, x0, x1, y0, y1, rc);
         for (uint32_t k = begin; k < end; k += 32)
         {
             const uint32_t e = k + lane;
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(256) k1_cull(const Rec *__restrict__ rec, cons
                 gi = (L.is_root || parent_idx == nullptr) ? e : parent_idx[e]; // no index array: the parent list is a contiguous range
                 const float4 a = cullrec[2 * gi]; // (oc.xyz, sigma)
                 const float4 cr = G.use_ref ? cullrec[2 * gi + 1] : make_float4(0.f, 0.f, 0.f, 1.f);
-                pass = cull_test(rc, a, a.w, cr);
+                pass = cull_test(G, rc, a, a.w, cr);
             }
             const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
             if (WRITE)
@@ -251,18 +259,17 @@ __global__ void k1_group_offsets(const uint32_t *__restrict__ seg_offsets, uint3
 
 // pure REFERENCE lists (one list per reference tile), level 1 with children = tiles
 template <bool WRITE>
-__global__ void __launch_bounds__(256) k1_cull_tiles(const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root,
+__global__ void __launch_bounds__(256) k1_cull_tiles(const FrameGeom G, const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root,
                                                      uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
                                                      uint32_t *__restrict__ out_idx, uint32_t n_tiles)
 {
     // one CTA per tile; ordered compaction across the CTA's 8 warps
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_base;
-    const FrameGeom &G = c_geom;
     const uint32_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
     const int tx = tile % G.tiles_x, ty = tile / G.tiles_x;
-    const float cx = c_tile_cx[tx], cy = c_tile_cy[ty];
+    const float cx = G.tile_cx[tx], cy = G.tile_cy[ty];
     const float hx = G.tw / 2, hy = G.th / 2;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = WRITE ? offsets[tile] : 0u;
@@ -298,20 +305,19 @@ __global__ void __launch_bounds__(256) k1_cull_tiles(const Rec *__restrict__ rec
 // centre ray (ties by Gaussian index, so the order is deterministic).  One warp per cell, bitonic network in shared memory;
 // lists longer than SORT_CAP stay in index order (the window test is valid for any order, it just saturates less often).
 constexpr int SORT_CAP = 512;
-__device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int &w, int &h);
-__global__ void __launch_bounds__(128) k1_sort_cells(const float4 *__restrict__ cullrec, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ list_idx,
+__device__ __forceinline__ void cell_rect(const FrameGeom &G, int cx, int cy, int &x0, int &y0, int &w, int &h);
+__global__ void __launch_bounds__(128) k1_sort_cells(const FrameGeom G, const float4 *__restrict__ cullrec, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ list_idx,
                                                      uint32_t n_cells)
 {
     __shared__ float s_key[4][SORT_CAP];
     __shared__ uint32_t s_val[4][SORT_CAP];
-    const FrameGeom &G = c_geom;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t cell = blockIdx.x * 4 + w;
     if (cell >= n_cells) return;
     const uint32_t off = list_off[cell], n = list_off[cell + 1] - off;
     if (n < 2 || n > SORT_CAP) return;
     int x0, y0, cw, ch;
-    cell_rect((int)(cell % G.ncx), (int)(cell / G.ncx), x0, y0, cw, ch);
+    cell_rect(G, (int)(cell % G.ncx), (int)(cell / G.ncx), x0, y0, cw, ch);
     // centre ray of the cell
     const float u = -1.f + ((float)x0 + 0.5f * (float)(cw - 1)) / G.half_w, v = -1.f + ((float)y0 + 0.5f * (float)(ch - 1)) / G.half_h;
     float d[3];
@@ -327,12 +333,15 @@ __global__ void __launch_bounds__(128) k1_sort_cells(const float4 *__restrict__ 
         {
             const uint32_t gi = list_idx[off + i];
             const float4 a = cullrec[2 * gi];
-            key[i] = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
+            // a non-finite or huge depth (overflowing centre, NaN) is clamped below the padding key, so the padding always
+            // stays behind every real entry and no 0xFFFFFFFF index can reach the first n slots
+            const float k = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
+            key[i] = (k == k) ? fminf(fmaxf(k, -2.9e38f), 2.9e38f) : 2.9e38f;
             val[i] = gi;
         }
         else
         {
-            key[i] = 3.0e38f;
+            key[i] = __int_as_float(0x7f800000); // +inf
             val[i] = 0xFFFFFFFFu;
         }
     }
@@ -458,19 +467,18 @@ struct TileStats
     unsigned long long n_big;      // queued items whose list is longer than the depth-window cache
     unsigned long long n_items;    // work items queued (cells + extra slices of split cells)
     unsigned long long n_split;    // items that belong to split cells (= partial-radiance slots)
+    unsigned long long terms_term; // K2b: terms dropped by the transmittance early exit
 };
 
-__device__ __forceinline__ uint32_t cell_list_id(int cx, int cy)
+__device__ __forceinline__ uint32_t cell_list_id(const FrameGeom &G, int cx, int cy)
 {
-    const FrameGeom &G = c_geom;
     if (G.list_kind == 0) return (uint32_t)(cy * G.ncx + cx);
     if (G.list_kind == 1) return (uint32_t)((cy / G.cpty) * G.tiles_x + (cx / G.cptx));
     return 0u;
 }
 
-__device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int &w, int &h)
+__device__ __forceinline__ void cell_rect(const FrameGeom &G, int cx, int cy, int &x0, int &y0, int &w, int &h)
 {
-    const FrameGeom &G = c_geom;
     if (G.uniform)
     {
         x0 = cx * CELL_W; y0 = cy * CELL_H;
@@ -485,20 +493,19 @@ __device__ __forceinline__ void cell_rect(int cx, int cy, int &x0, int &y0, int 
 }
 
 // number of work items of a cell with an n-entry list
-__device__ __forceinline__ uint32_t cell_items(uint32_t n, uint32_t cell)
+__device__ __forceinline__ uint32_t cell_items(const FrameGeom &G, uint32_t n, uint32_t cell)
 {
-    const uint32_t slice = (uint32_t)c_geom.slice;
+    const uint32_t slice = (uint32_t)G.slice;
     if (n <= 3u * slice || cell >= (1u << ITEM_CELL_BITS)) return 1u;
     const uint32_t k = (n + slice - 1) / slice;
     return k <= (1u << (32 - ITEM_CELL_BITS)) ? k : 1u;
 }
 
-// COUNT_ITEMS = false: listed terms and per-row cost; true: work items per list-length key (needs c_geom.slice)
+// COUNT_ITEMS = false: listed terms and per-row cost; true: work items per list-length key (needs the frame's slice size)
 template <bool COUNT_ITEMS>
-__global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
+__global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
                         double *__restrict__ row_cost, int cy_begin, int cy_end)
 {
-    const FrameGeom &G = c_geom;
     const int ncells = (cy_end - cy_begin) * G.ncx;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double terms = 0.0;
@@ -506,15 +513,15 @@ __global__ void k1_hist(const uint32_t *__restrict__ list_off, uint32_t *__restr
     {
         const int cx = i % G.ncx, cy = cy_begin + i / G.ncx;
         int x0, y0, w, h;
-        cell_rect(cx, cy, x0, y0, w, h);
+        cell_rect(G, cx, cy, x0, y0, w, h);
         const int ya = max(y0, G.row_begin), yb = min(y0 + h, G.row_end);
-        const uint32_t id = cell_list_id(cx, cy);
+        const uint32_t id = cell_list_id(G, cx, cy);
         const uint32_t n = list_off[id + 1] - list_off[id];
         if (yb > ya)
         {
             if (COUNT_ITEMS)
             {
-                const uint32_t items = cell_items(n, (uint32_t)(cy * G.ncx + cx));
+                const uint32_t items = cell_items(G, n, (uint32_t)(cy * G.ncx + cx));
                 atomicAdd(&hist[min(n, 65535u)], items);
                 atomicAdd(&stats->n_items, (unsigned long long)items);
                 if (items > 1) atomicAdd(&stats->n_split, (unsigned long long)items);
@@ -580,21 +587,20 @@ __global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist
     }
 }
 
-__global__ void k1_order(const uint32_t *__restrict__ list_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, uint32_t *__restrict__ cell_slot,
+__global__ void k1_order(const FrameGeom G, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, uint32_t *__restrict__ cell_slot,
                          uint32_t *__restrict__ split_cursor, int cy_begin, int cy_end)
 {
-    const FrameGeom &G = c_geom;
     const int ncells = (cy_end - cy_begin) * G.ncx;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncells) return;
     const int cx = i % G.ncx, cy = cy_begin + i / G.ncx;
     int x0, y0, w, h;
-    cell_rect(cx, cy, x0, y0, w, h);
+    cell_rect(G, cx, cy, x0, y0, w, h);
     if (min(y0 + h, G.row_end) <= max(y0, G.row_begin)) return;
-    const uint32_t id = cell_list_id(cx, cy);
+    const uint32_t id = cell_list_id(G, cx, cy);
     const uint32_t n = list_off[id + 1] - list_off[id];
     const uint32_t cell = (uint32_t)(cy * G.ncx + cx);
-    const uint32_t items = cell_items(n, cell);
+    const uint32_t items = cell_items(G, n, cell);
     const uint32_t pos = atomicAdd(&cursor[min(n, 65535u)], items);
     for (uint32_t k = 0; k < items; ++k) queue[pos + k] = cell | (k << ITEM_CELL_BITS);
     // split cells get `items` consecutive slots of the partial-radiance buffer (the slot order is irrelevant: K3' sums a

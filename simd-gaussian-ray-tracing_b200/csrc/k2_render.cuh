@@ -1,6 +1,5 @@
 // k2_render.cuh -- K2 + K3: the render kernel (one warp per 8x4-pixel cell), pixel packing, the combine pass of split cells.
-// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace (one translation unit, so
-// every kernel sees the same __constant__ frame geometry).  Not a stand-alone header.
+// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace.  Not a stand-alone header.
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
@@ -8,6 +7,7 @@
 // ------------------------------------------------------------------------------------------------
 struct RenderArgs
 {
+    FrameGeom geom;            // the frame (by value: nothing about a frame lives in per-device state)
     const Rec *rec;            // frame records
     const uint32_t *list_off;  // per list: [off, off+n)
     const uint32_t *list_idx;  // indices into rec, or nullptr when lists are contiguous ranges of rec
@@ -18,9 +18,13 @@ struct RenderArgs
     float4 *radiance;          // W*H float4 (may be null)
     unsigned long long *terms_exec;
     unsigned long long *terms_sat;
+    unsigned long long *terms_term;  // terms dropped by the transmittance early exit (k2_band)
+    const uint32_t *scene_info;      // K0: [0] max |albedo| (float bits), [1] != 0: non-monotone scene, no early exit
+    const volatile uint32_t *abort_flag; // mapped host word, or null: != 0 -> the persistent warps stop taking work (`running` went false)
+    uint32_t terminate;              // early exit enabled
     float skip_thresh;         // skip an occluder / emitter for the whole warp when exp2 weight <= thresh (-1: never)
     uint32_t quant_nearest, alpha_from_w;
-    uint32_t window; // depth-window mode
+    uint32_t window; // banded evaluation of depth-sorted lists (k2_band; k2_render<WIN> for lists beyond its cache)
     const uint32_t *cell_slot; // per cell: first slot of its slices in `partial`, NO_SLOT for whole cells (may be null)
     float4 *partial;           // [slot][lane] partial radiance of the items of split cells
 };
@@ -103,9 +107,8 @@ __device__ __forceinline__ void store_pixel(const RenderArgs &args, size_t pi, f
 }
 
 // ray through pixel (px, py): plane = inverse(view) (u, v, 0, 1) (src/vrt/camera.cpp:60-70); dir = normalize(plane - origin)
-__device__ __forceinline__ PixelRay pixel_ray(int px, int py)
+__device__ __forceinline__ PixelRay pixel_ray(const FrameGeom &G, int px, int py)
 {
-    const FrameGeom &G = c_geom;
     const float u = -1.f + (float)px / G.half_w, v = -1.f + (float)py / G.half_h;
     const float dx = (G.inv0[0] * u + G.inv1[0] * v) + G.inv3[0] - G.origin[0];
     const float dy = (G.inv0[1] * u + G.inv1[1] * v) + G.inv3[1] - G.origin[1];
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
     constexpr int CTA_WARPS = k2_cta_warps(Q, MINB);
     __shared__ __align__(128) Rec s_rec[CTA_WARPS][2][STAGE];
     __shared__ __align__(8) unsigned long long s_bar[CTA_WARPS][2];
-    const FrameGeom &G = c_geom;
+    const FrameGeom &G = args.geom;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & (CELL_W - 1), ly = lane >> 3;
     unsigned long long exec = 0, sat = 0;
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 
     for (;;)
     {
+        if (args.abort_flag && *args.abort_flag) break; // interrupted render (`running` went false, rt.h:244-246, 289)
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(args.counter, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
@@ -151,14 +155,14 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
         const uint32_t cell = item & ((1u << ITEM_CELL_BITS) - 1u), slice = item >> ITEM_CELL_BITS;
         const int cx = cell % G.ncx, cy = cell / G.ncx;
         int x0, y0, cw, ch;
-        cell_rect(cx, cy, x0, y0, cw, ch);
+        cell_rect(G, cx, cy, x0, y0, cw, ch);
         const int px = x0 + min(lx, cw - 1), py = y0 + min(ly, ch - 1);
         const bool live = lx < cw && ly < ch && py >= G.row_begin && py < G.row_end;
         const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
 
-        const PixelRay ray = pixel_ray(px, py);
+        const PixelRay ray = pixel_ray(G, px, py);
 
-        const uint32_t lid = cell_list_id(cx, cy);
+        const uint32_t lid = cell_list_id(G, cx, cy);
         const uint32_t off = args.list_off[lid];
         const uint32_t n = args.list_off[lid + 1] - off;
 
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 // K3', split cells: sum the slices' partial radiances in slice order (deterministic) and write the pixel.
 __global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, const uint32_t *__restrict__ list_off, int cy_begin, int cy_end)
 {
-    const FrameGeom &G = c_geom;
+    const FrameGeom &G = args.geom;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t ncells = (uint32_t)((cy_end - cy_begin) * G.ncx);
@@ -380,12 +384,12 @@ __global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, const u
     const int cx = (int)(w % G.ncx), cy = cy_begin + (int)(w / G.ncx);
     const uint32_t cell = (uint32_t)(cy * G.ncx + cx);
     int x0, y0, cw, ch;
-    cell_rect(cx, cy, x0, y0, cw, ch);
+    cell_rect(G, cx, cy, x0, y0, cw, ch);
     if (min(y0 + ch, G.row_end) <= max(y0, G.row_begin)) return; // not queued: its slot entry is stale
     const uint32_t slot = args.cell_slot[cell];
     if (slot == NO_SLOT) return;
-    const uint32_t lid = cell_list_id(cx, cy);
-    const uint32_t items = cell_items(list_off[lid + 1] - list_off[lid], cell);
+    const uint32_t lid = cell_list_id(G, cx, cy);
+    const uint32_t items = cell_items(G, list_off[lid + 1] - list_off[lid], cell);
     float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t k = 0; k < items; ++k)
     {

@@ -1,6 +1,5 @@
 // k2_variant.cuh -- K2'': the reference's alternative erf / exp approximations as device functions and the kernel that renders with them.
-// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace (one translation unit, so
-// every kernel sees the same __constant__ frame geometry).  Not a stand-alone header.
+// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace.  Not a stand-alone header.
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
@@ -102,12 +101,13 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_variant(const RenderArgs arg
 {
     __shared__ ApproxTables s_tab;
     load_tables(s_tab);
-    const FrameGeom &G = c_geom;
+    const FrameGeom &G = args.geom;
     const int lane = threadIdx.x & 31;
     const int lx = lane & (CELL_W - 1), ly = lane >> 3;
     constexpr float LN2 = 1.f / LOG2E;
     for (;;)
     {
+        if (args.abort_flag && *args.abort_flag) break; // interrupted render
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(args.counter, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_variant(const RenderArgs arg
         const uint32_t cell = item & ((1u << ITEM_CELL_BITS) - 1u), slice = item >> ITEM_CELL_BITS;
         const int cx = cell % G.ncx, cy = cell / G.ncx;
         int x0, y0, cw, ch;
-        cell_rect(cx, cy, x0, y0, cw, ch);
+        cell_rect(G, cx, cy, x0, y0, cw, ch);
         const int px = x0 + min(lx, cw - 1), py = y0 + min(ly, ch - 1);
         const bool live = lx < cw && ly < ch && py >= G.row_begin && py < G.row_end;
         const uint32_t n_live = __popc(__ballot_sync(0xffffffffu, live));
-        const PixelRay ray = pixel_ray(px, py);
-        const uint32_t lid = cell_list_id(cx, cy);
+        const PixelRay ray = pixel_ray(G, px, py);
+        const uint32_t lid = cell_list_id(G, cx, cy);
         const uint32_t off = args.list_off[lid];
         const uint32_t n = args.list_off[lid + 1] - off;
         auto load_rec = [&](uint32_t k) -> const Rec * { return args.rec + (args.list_idx ? args.list_idx[off + k] : off + k); };

@@ -1,6 +1,5 @@
 // probes.cuh -- roofline probes: FP32 FMA peak, inner-term ceiling, pipe-mix chains.
-// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace (one translation unit, so
-// every kernel sees the same __constant__ frame geometry).  Not a stand-alone header.
+// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace.  Not a stand-alone header.
 #pragma once
 
 // ------------------------------------------------------------------------------------------------

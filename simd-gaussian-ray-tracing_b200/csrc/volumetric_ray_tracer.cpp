@@ -214,6 +214,9 @@ int main(int argc, char **argv)
 
     const uint32_t width = (uint32_t)cmd.w, height = (uint32_t)cmd.h;
     std::vector<uint32_t> image((size_t)width * height, 0u);
+    // the frame buffer lives as long as the process (main.cpp:245, 338): page-lock it once so that every frame's copy-back
+    // runs at PCIe rate (not fatal if the system refuses)
+    const bool pinned = vrt_cuda_pin_buffer(ctx[0], image.data(), image.size() * sizeof(uint32_t)) == VRT_CUDA_OK;
     const uint32_t flags = (mode_flags(cmd.mode) & ~cmd.approx_clear) | cmd.approx_set;
     const bool tiled = (flags & VRT_CUDA_LIST_MASK) == VRT_CUDA_LIST_REFERENCE || (flags & VRT_CUDA_LIST_MASK) == VRT_CUDA_LIST_REFERENCE_BOUND;
 
@@ -298,6 +301,7 @@ int main(int argc, char **argv)
         if (cmd.nr_frames == frame && cmd.nr_frames > 1) std::printf("AVG. TIME: %g ms (%llu frames)\n", total_time / cmd.nr_frames, (unsigned long long)cmd.nr_frames);
         angle += cmd.rot / cmd.nr_frames; // main.cpp:330
     }
+    if (pinned) vrt_cuda_unpin_buffer(ctx[0], image.data());
     for (vrt_cuda_ctx *c : ctx) vrt_cuda_destroy(c);
     return EXIT_SUCCESS;
 }

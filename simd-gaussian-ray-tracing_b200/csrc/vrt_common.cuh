@@ -1,6 +1,6 @@
-// vrt_common.cuh -- constants, the frame geometry in constant memory, the per-Gaussian record and the erf device functions.
-// A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace (one translation unit, so
-// every kernel sees the same __constant__ frame geometry).  Not a stand-alone header.
+// vrt_common.cuh -- constants, the frame geometry (a kernel ARGUMENT: no per-device state), the per-Gaussian record and the
+// erf device functions.  A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace.
+// Not a stand-alone header.
 #pragma once
 
 constexpr int CELL_W = 8;          // pixels per cell (= one warp), x
@@ -47,11 +47,11 @@ struct FrameGeom
     float bound_k;
     float tw, th;     // 2/tiles
     float half_w, half_h; // W/2, H/2 as float
+    // float-accumulated tile centres (src/vrt/rt.cpp:47-49): 1024 + 1024 floats in the context's own device buffer
+    const float *tile_cx, *tile_cy;
 };
-
-__constant__ FrameGeom c_geom;
-__constant__ float c_tile_cx[1024]; // float-accumulated tile centres (src/vrt/rt.cpp:47-49)
-__constant__ float c_tile_cy[1024];
+// The geometry travels by value in every kernel's parameter block (the frame is stateless on the device: two contexts, or
+// two frames of one context, can be in flight on the same GPU -- the re-entrancy of the reference's entries).
 
 // per-Gaussian frame record: 3 x float4
 //   a = (oc.x, oc.y, oc.z, (mu.w - o.w)^2)            oc = mu - origin

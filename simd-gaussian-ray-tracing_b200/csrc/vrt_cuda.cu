@@ -12,8 +12,10 @@
 // the render kernel.  See DESIGN.md for the algebra (sample-invariant terms hoisted out of the n^2 loop) and
 // the roofline.
 //
-// Layout: vrt_common.cuh (constants, records, erf) / k1_tile.cuh (K0, K1) / k2_render.cuh (K2, K3) / k2_window.cuh /
-// k2_variant.cuh / probes.cuh are fragments of this translation unit; this file holds the context, the launch logic and the C ABI.
+// Layout: vrt_common.cuh (constants, records, erf) / k1_tile.cuh (K0, K1) / k2_render.cuh (K2, K3) / k2_band.cuh (K2b, the
+// default kernel on depth-sorted lists) / k2_variant.cuh / probes.cuh are fragments of this translation unit; this file holds
+// the context, the launch logic and the C ABI.  Nothing about a frame lives in per-device state (no __constant__ geometry):
+// contexts are independent even on one GPU.
 //
 // No CPU fallback: every entry point fails without a CUDA device.  Nothing under oracle/ is used here.
 #include "vrt_cuda.h"
@@ -26,11 +28,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
-// device code: one translation unit (a single copy of the __constant__ frame geometry), split by kernel family
+// device code: one translation unit, split by kernel family
 // ------------------------------------------------------------------------------------------------
 namespace
 {
@@ -38,7 +42,7 @@ namespace
 #include "k1_tile.cuh"
 #include "k2_render.cuh"
 #include "k2_variant.cuh"
-#include "k2_window.cuh"
+#include "k2_band.cuh"
 #include "probes.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -68,6 +72,20 @@ struct vrt_cuda_ctx
     DevBuf lvl_counts[4], lvl_offsets[4], lvl_idx[4], lvl_group_off; // coarse culling levels
     DevBuf ccounts, coffsets, cidx;       // level 1 (cells / tiles)
     DevBuf hist, queue, stats, counter, rowcost, scan_tmp, cell_slot, partial;
+    DevBuf tile_centres; // 2 x 1024 floats: the reference's float-accumulated tile centres of the current frame
+    DevBuf scene_info;   // K0: max |albedo| bits, non-monotone flag
+    // interruption: the persistent render warps poll a word in DEVICE memory (an L2 hit per work item, not a PCIe read);
+    // vrt_cuda_abort writes it from any thread with a 4-byte copy on a stream of its own, which overlaps the running kernel
+    uint32_t *abort_host = nullptr; // pinned staging word
+    uint32_t *abort_dev = nullptr;
+    cudaStream_t abort_stream = nullptr;
+    // caller buffers this context page-locked (cudaHostRegister) so that the copies of vrt_cuda_set_gaussians /
+    // vrt_cuda_render run at PCIe speed instead of through the driver's staging buffer: the reference's callers hand in
+    // plain aligned_malloc memory (main.cpp:245) and reuse it every frame
+    struct Pinned { void *ptr = nullptr; size_t bytes = 0; };
+    Pinned pinned[4];
+    int pinned_next = 0;
+    int pin_mode = 0; // opt-in (vrt_cuda_set_host_pinning): the caller promises its buffers outlive the registration
     DevBuf out_image, out_rad;
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
     DevBuf tile_off;
@@ -78,7 +96,6 @@ struct vrt_cuda_ctx
     bool lists_from_host = false;
     bool lists_sorted = false;
     uint32_t n_big = 0, n_split = 0;
-    bool win_attr[2] = {false, false};
     FrameGeom geom{};
     uint32_t n_lists = 0;
     uint64_t n_entries = 0;
@@ -99,6 +116,10 @@ struct vrt_cuda_ctx
     int tune_slice = 0; // 0 = automatic (auto_slice)
     int tune_q = 0; // 0 = automatic: 8 emitters per register block, 4 when the lists are short
     int tune_pack = 1;
+    std::vector<float> centres_host;
+    uint32_t tiled_list_mode = 0; // what the current lists were built for (vrt_cuda_render_device checks the frame against it)
+    int tiled_tiles_x = 0, tiled_tiles_y = 0;
+    float tiled_bound = 0.f;
 };
 
 namespace
@@ -226,11 +247,17 @@ int make_geom(vrt_cuda_ctx *ctx, const vrt_cuda_frame *f, int list_kind_override
     return 0;
 }
 
-int upload_geom(vrt_cuda_ctx *ctx, const FrameGeom &G, const std::vector<float> &cxs, const std::vector<float> &cys)
+// The tile centres go to the context's own device buffer (stream-ordered after the previous frame's kernels); the geometry
+// itself is a kernel argument.
+int upload_geom(vrt_cuda_ctx *ctx, FrameGeom &G, const std::vector<float> &cxs, const std::vector<float> &cys)
 {
-    CU(cudaMemcpyToSymbolAsync(c_geom, &G, sizeof(G), 0, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyToSymbolAsync(c_tile_cx, cxs.data(), sizeof(float) * 1024, 0, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyToSymbolAsync(c_tile_cy, cys.data(), sizeof(float) * 1024, 0, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = reserve(ctx, ctx->tile_centres, sizeof(float) * 2048)) return rc;
+    ctx->centres_host.resize(2048);
+    std::memcpy(ctx->centres_host.data(), cxs.data(), sizeof(float) * 1024);
+    std::memcpy(ctx->centres_host.data() + 1024, cys.data(), sizeof(float) * 1024);
+    CU(cudaMemcpyAsync(ctx->tile_centres.p, ctx->centres_host.data(), sizeof(float) * 2048, cudaMemcpyHostToDevice, ctx->stream));
+    G.tile_cx = (const float *)ctx->tile_centres.p;
+    G.tile_cy = G.tile_cx + 1024;
     return 0;
 }
 
@@ -293,7 +320,7 @@ int build_queue(vrt_cuda_ctx *ctx)
     const uint32_t *loff = (const uint32_t *)ctx->coffsets.p;
     const int tb = 256, gb = (ncells + tb - 1) / tb;
     k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(loff, ctx->n_lists, (TileStats *)ctx->stats.p);
-    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
+    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(G, loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
     TileStats ts;
     CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -303,9 +330,8 @@ int build_queue(vrt_cuda_ctx *ctx)
         ctx->q_terms_listed = ts.terms_listed;
         ctx->q_max_list = (uint32_t)ts.max_list;
         ctx->geom.slice = ctx->tune_slice ? ctx->tune_slice : auto_slice(ctx, 1.0);
-        CU(cudaMemcpyToSymbolAsync(c_geom, &ctx->geom, sizeof(FrameGeom), 0, cudaMemcpyHostToDevice, ctx->stream));
     }
-    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, nullptr, cyb, cye);
+    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(G, loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, nullptr, cyb, cye);
     k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p);
     // descending order: the start slot of key WIN_CAP = number of items with a longer list (they lead the queue)
     CU(cudaMemcpyAsync(&((TileStats *)ctx->stats.p)->n_big, (const uint32_t *)ctx->hist.p + WIN_CAP, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -318,7 +344,7 @@ int build_queue(vrt_cuda_ctx *ctx)
     if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max<uint32_t>(ctx->n_queue, 1))) return rc;
     if (int rc = reserve(ctx, ctx->cell_slot, sizeof(uint32_t) * (size_t)G.ncx * G.ncy)) return rc;
     CU(cudaMemsetAsync((uint32_t *)ctx->counter.p + 2, 0, sizeof(uint32_t), ctx->stream));
-    k1_order<<<gb, tb, 0, ctx->stream>>>(loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye);
+    k1_order<<<gb, tb, 0, ctx->stream>>>(G, loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye);
     ctx->launches += 5;
     CU(cudaGetLastError());
     return 0;
@@ -357,9 +383,9 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     const bool p = ctx->tune_pack != 0;
     if (a.window)
     {
-        // depth-window mode (depth-sorted index lists).  The queue is in descending list length, so the cells whose list
-        // does not fit the per-warp cache of k2_window lead it: they go to k2_render's in-loop saturation test, the rest
-        // to k2_window.
+        // banded evaluation (depth-sorted index lists).  The queue is in descending list length, so the cells whose list
+        // does not fit the per-warp cache of k2_band lead it: they go to k2_render's in-loop saturation test, the rest
+        // to k2_band.
         const uint32_t n_big = std::min(ctx->n_big, a.n_queue);
         if (n_big)
         {
@@ -370,15 +396,12 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
         }
         if (a.n_queue > n_big)
         {
-            const size_t smem = sizeof(WinSmem) * K2_WARPS;
-            if (!ctx->win_attr[ERF]) // per device: the opt-in for > 48 KB of dynamic shared memory
-            {
-                cudaFuncSetAttribute(k2_window<ERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                ctx->win_attr[ERF] = true;
-            }
-            const uint32_t want = (a.n_queue - n_big + K2_WARPS - 1) / K2_WARPS;
-            const uint32_t grid = std::max(1u, std::min(want, (uint32_t)ctx->sm_count));
-            k2_window<ERF><<<grid, K2_WARPS * 32, smem, ctx->stream>>>(a, n_big);
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band<ERF>, BAND_WARPS * 32, 0);
+            if (per_sm < 1) per_sm = 1;
+            const uint32_t want = (a.n_queue - n_big + BAND_WARPS - 1) / BAND_WARPS;
+            const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
+            k2_band<ERF><<<grid, BAND_WARPS * 32, 0, ctx->stream>>>(a, n_big);
         }
         return 0;
     }
@@ -496,6 +519,17 @@ int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
         vrt_cuda_destroy(c);
         return VRT_CUDA_E_CUDA;
     }
+    // the word the persistent render warps poll (see vrt_cuda_abort)
+    if (cudaHostAlloc((void **)&c->abort_host, sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc((void **)&c->abort_dev, sizeof(uint32_t)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->abort_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMemset(c->abort_dev, 0, sizeof(uint32_t)) != cudaSuccess)
+    {
+        g_create_error = "cannot allocate the abort word";
+        vrt_cuda_destroy(c);
+        return VRT_CUDA_E_CUDA;
+    }
+    *c->abort_host = 0u;
     *ctx_out = c;
     return 0;
 }
@@ -505,7 +539,12 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
+    for (auto &r : ctx->pinned)
+        if (r.ptr) cudaHostUnregister(r.ptr);
+    if (ctx->abort_stream) { cudaStreamSynchronize(ctx->abort_stream); cudaStreamDestroy(ctx->abort_stream); }
+    if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
+    if (ctx->abort_dev) cudaFree(ctx->abort_dev);
+    DevBuf *bufs[] = {&ctx->tile_centres, &ctx->scene_info, &ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
                       &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off, &ctx->lit_offsets, &ctx->lit_idx};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -565,6 +604,81 @@ int vrt_cuda_sync(vrt_cuda_ctx *ctx)
     return 0;
 }
 
+// Page-lock a caller buffer once per (pointer, size); the registration is kept until the slot is reused or the context is
+// destroyed.  Failure is not an error: the copy then takes the driver's staged path.
+static void pin_host(vrt_cuda_ctx *ctx, const void *p, size_t bytes)
+{
+    if (!ctx->pin_mode || !p || bytes < (1u << 20)) return;
+    for (auto &r : ctx->pinned)
+        if (r.ptr == p && r.bytes >= bytes) return;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return; // already pinned / managed by the caller
+    cudaGetLastError();
+    auto &slot = ctx->pinned[ctx->pinned_next];
+    if (slot.ptr)
+    {
+        cudaStreamSynchronize(ctx->stream);
+        cudaHostUnregister(slot.ptr);
+        slot = vrt_cuda_ctx::Pinned{};
+    }
+    // registration covers whole pages
+    const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
+    if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable) == cudaSuccess)
+    {
+        slot.ptr = (void *)lo;
+        slot.bytes = hi - lo;
+        ctx->pinned_next = (ctx->pinned_next + 1) % 4;
+    }
+    else cudaGetLastError();
+}
+
+int vrt_cuda_set_host_pinning(vrt_cuda_ctx *ctx, int on)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    ctx->pin_mode = on ? 1 : 0;
+    if (!on)
+    {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &r : ctx->pinned)
+        {
+            if (r.ptr) cudaHostUnregister(r.ptr);
+            r = vrt_cuda_ctx::Pinned{};
+        }
+    }
+    return 0;
+}
+
+int vrt_cuda_pin_buffer(vrt_cuda_ctx *ctx, void *p, uint64_t bytes)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!p || !bytes) return fail(ctx, VRT_CUDA_E_INVALID, "nothing to pin");
+    CU(cudaSetDevice(ctx->device));
+    const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
+    CU(cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable));
+    return 0;
+}
+
+int vrt_cuda_unpin_buffer(vrt_cuda_ctx *ctx, void *p)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaHostUnregister((void *)((uintptr_t)p & ~(uintptr_t)4095)));
+    return 0;
+}
+
+int vrt_cuda_abort(vrt_cuda_ctx *ctx, int on)
+{
+    if (!ctx || !ctx->abort_host) return VRT_CUDA_E_INVALID;
+    // (no `CU`: this may run on a thread other than the one driving the context, and must not touch ctx->err)
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return VRT_CUDA_E_CUDA;
+    *ctx->abort_host = on ? 1u : 0u;
+    if (cudaMemcpyAsync(ctx->abort_dev, ctx->abort_host, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->abort_stream) != cudaSuccess) return VRT_CUDA_E_CUDA;
+    if (cudaStreamSynchronize(ctx->abort_stream) != cudaSuccess) return VRT_CUDA_E_CUDA;
+    return 0;
+}
+
 static int set_gaussians_impl(vrt_cuda_ctx *ctx, const float *aos, uint64_t n, cudaMemcpyKind kind)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
@@ -572,7 +686,10 @@ static int set_gaussians_impl(vrt_cuda_ctx *ctx, const float *aos, uint64_t n, c
     if (n > 0x7FFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "too many Gaussians (device indices are 32-bit, cull records are addressed as 2 * index)");
     CU(cudaSetDevice(ctx->device));
     if (int rc = reserve(ctx, ctx->aos, std::max<size_t>(n, 1) * 40)) return rc;
+    if (n && kind == cudaMemcpyHostToDevice) pin_host(ctx, aos, n * 40);
     if (n) CU(cudaMemcpyAsync(ctx->aos.p, aos, n * 40, kind, ctx->stream));
+    // a copy out of page-locked memory is truly asynchronous: the caller may reuse `aos` as soon as this returns
+    if (n && kind == cudaMemcpyHostToDevice && ctx->pin_mode) CU(cudaStreamSynchronize(ctx->stream));
     ctx->n_gauss = n;
     ctx->have_lists = false;
     return 0;
@@ -724,17 +841,20 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     ctx->have_lists = false;
     ctx->lists_from_host = false;
     ctx->literal = false;
-    ctx->geom = G;
     ctx->launches = 0;
     const uint64_t N = ctx->n_gauss;
     if (int rc = upload_geom(ctx, G, cxs, cys)) return rc;
+    ctx->geom = G;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 
     if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(N, 1))) return rc;
     if (int rc = reserve(ctx, ctx->cullrec, 2 * sizeof(float4) * std::max<uint64_t>(N, 1))) return rc;
+    if (int rc = reserve(ctx, ctx->scene_info, sizeof(uint32_t) * 4)) return rc;
+    CU(cudaMemsetAsync(ctx->scene_info.p, 0, sizeof(uint32_t) * 4, ctx->stream));
     if (N)
     {
-        k0_prepare<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->aos.p, N, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p);
+        k0_prepare<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(G, (const float *)ctx->aos.p, N, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p,
+                                                                         (uint32_t *)ctx->scene_info.p);
         ctx->launches++;
     }
 
@@ -753,13 +873,13 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
         const uint32_t nt = (uint32_t)(G.tiles_x * G.tiles_y);
         if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * nt)) return rc;
         if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (nt + 1))) return rc;
-        k1_cull_tiles<false><<<nt, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, (uint32_t *)ctx->ccounts.p, nullptr, nullptr, nt);
+        k1_cull_tiles<false><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, (uint32_t *)ctx->ccounts.p, nullptr, nullptr, nt);
         k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, nt);
         uint32_t total = 0;
         CU(cudaMemcpyAsync(&total, (const uint32_t *)ctx->coffsets.p + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
-        k1_cull_tiles<true><<<nt, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nullptr, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, nt);
+        k1_cull_tiles<true><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nullptr, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, nt);
         ctx->launches += 3;
         ctx->n_lists = nt;
         ctx->n_entries = total;
@@ -803,14 +923,14 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
             if (int rc = reserve(ctx, cnt, sizeof(uint32_t) * work)) return rc;
             if (int rc = reserve(ctx, off, sizeof(uint32_t) * (work + 1))) return rc;
             const unsigned grid = (unsigned)((work * 32 + 255) / 256);
-            k1_cull<false><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx,
+            k1_cull<false><<<grid, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx,
                                                          (uint32_t *)cnt.p, nullptr, nullptr, (uint32_t)work);
             if (int rc = scan_u32(ctx, (const uint32_t *)cnt.p, (uint32_t *)off.p, (uint32_t)work)) return rc;
             uint32_t total = 0;
             CU(cudaMemcpyAsync(&total, (const uint32_t *)off.p + work, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             if (int rc = reserve(ctx, idx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
-            k1_cull<true><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx, nullptr,
+            k1_cull<true><<<grid, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx, nullptr,
                                                         (const uint32_t *)off.p, (uint32_t *)idx.p, (uint32_t)work);
             ctx->launches += 2;
             parent_idx = (const uint32_t *)idx.p;
@@ -835,12 +955,16 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
             }
         }
     }
+    ctx->tiled_list_mode = frame->flags & VRT_CUDA_LIST_MASK;
+    ctx->tiled_tiles_x = G.tiles_x;
+    ctx->tiled_tiles_y = G.tiles_y;
+    ctx->tiled_bound = G.bound_k;
     ctx->lists_sorted = false;
     // bounded per-cell lists are always depth-sorted: the order is deterministic (ties by index) and makes most occluders
     // sign-uniform for an emitter block (K2), and saturated in depth-window mode
     if (G.list_kind == 0 && ctx->n_entries)
     {
-        k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
+        k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>(ctx->geom, (const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
         ctx->launches++;
         ctx->lists_sorted = true;
     }
@@ -887,6 +1011,7 @@ int vrt_cuda_tile(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     ctx->ms_tile += ms_literal;
     ctx->launches += launches_literal;
     ctx->literal = true;
+    ctx->tiled_list_mode = lm; // what the caller asked for (the visible subsets are an implementation detail)
     return 0;
 }
 
@@ -910,10 +1035,12 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
     }
     ctx->have_lists = false;
     ctx->literal = false;
-    ctx->geom = G;
     ctx->launches = 0;
     if (int rc = upload_geom(ctx, G, cxs, cys)) return rc;
+    ctx->geom = G;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (int rc = reserve(ctx, ctx->scene_info, sizeof(uint32_t) * 4)) return rc;
+    CU(cudaMemsetAsync(ctx->scene_info.p, 0, sizeof(uint32_t) * 4, ctx->stream));
     if (int rc = reserve(ctx, ctx->tile_aos, std::max<uint64_t>(total, 1) * 40)) return rc;
     if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(total, 1))) return rc;
     if (int rc = reserve(ctx, ctx->cullrec, 2 * sizeof(float4) * std::max<uint64_t>(total, 1))) return rc;
@@ -922,7 +1049,8 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
     CU(cudaMemcpyAsync(ctx->coffsets.p, off32.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (total)
     {
-        k0_prepare<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float *)ctx->tile_aos.p, total, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p);
+        k0_prepare<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(G, (const float *)ctx->tile_aos.p, total, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p,
+                                                                             (uint32_t *)ctx->scene_info.p);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -941,8 +1069,7 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
         V.use_ref = 0;
         V.use_bound = 1;
         V.bound_k = VISIBLE_SIGMAS;
-        ctx->geom = V;
-        if (int rc = upload_geom(ctx, V, cxs, cys)) return rc;
+        ctx->geom = V; // (same tile-centre buffer)
         CullLevel L{};
         L.gx = L.gy = 1;
         L.ngx = V.ncx; L.ngy = V.ncy;
@@ -953,21 +1080,21 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
         if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * cells)) return rc;
         if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (cells + 1))) return rc;
         const unsigned grid = (unsigned)((cells * 32 + 255) / 256);
-        k1_cull<false><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr,
+        k1_cull<false><<<grid, 256, 0, ctx->stream>>>(V, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr,
                                                      (uint32_t *)ctx->ccounts.p, nullptr, nullptr, (uint32_t)cells);
         if (int rc = scan_u32(ctx, (const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, (uint32_t)cells)) return rc;
         uint32_t kept = 0;
         CU(cudaMemcpyAsync(&kept, (const uint32_t *)ctx->coffsets.p + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(kept, 1))) return rc;
-        k1_cull<true><<<grid, 256, 0, ctx->stream>>>((const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr, nullptr,
+        k1_cull<true><<<grid, 256, 0, ctx->stream>>>(V, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr, nullptr,
                                                     (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, (uint32_t)cells);
         ctx->launches += 2;
         ctx->n_lists = (uint32_t)cells;
         ctx->n_entries = kept;
         if (kept)
         {
-            k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>((const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
+            k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>(ctx->geom, (const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
             ctx->launches++;
             ctx->lists_sorted = true;
         }
@@ -1037,6 +1164,29 @@ int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, u
     return 0;
 }
 
+// statistics of the last tile + render (waits for the stream)
+static int read_stats(vrt_cuda_ctx *ctx, vrt_cuda_stats *stats)
+{
+    TileStats ts;
+    CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::memset(stats, 0, sizeof(*stats));
+    stats->n_gaussians = ctx->n_gauss;
+    stats->n_cells = ctx->literal ? ctx->lit_n_lists : ctx->n_lists;
+    stats->list_entries = ctx->literal ? ctx->lit_stats.entries : ts.entries;
+    stats->max_list = (uint32_t)(ctx->literal ? ctx->lit_stats.max_list : ts.max_list);
+    stats->n_launches = ctx->launches + ctx->render_launches;
+    stats->terms_listed = ctx->literal ? ctx->lit_stats.terms_listed : ts.terms_listed;
+    stats->terms_executed = (double)ts.terms_exec;
+    stats->terms_saturated = (double)ts.terms_sat;
+    stats->terms_terminated = (double)ts.terms_term;
+    stats->ms_tile = ctx->ms_tile;
+    CU(cudaEventElapsedTime(&stats->ms_render, ctx->ev[2], ctx->ev[3]));
+    stats->ms_total = stats->ms_tile + stats->ms_render;
+    stats->slice = (uint32_t)ctx->geom.slice;
+    return 0;
+}
+
 int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image_dev, float *radiance_dev, vrt_cuda_stats *stats)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
@@ -1052,11 +1202,24 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
         const int re = (frame->row_begin == 0 && frame->row_end == 0) ? G.H : (int)frame->row_end;
         if (rb != G.row_begin || re != G.row_end) return fail(ctx, VRT_CUDA_E_STATE, "row band differs from the tiled frame");
     }
+    if (!ctx->lists_from_host)
+    {
+        // the lists belong to one list mode, tile count and bound: a frame that names another one would render with semantics
+        // its flags do not describe
+        const uint32_t lm = frame->flags & VRT_CUDA_LIST_MASK;
+        const bool tiled = lm == VRT_CUDA_LIST_REFERENCE || lm == VRT_CUDA_LIST_REFERENCE_BOUND;
+        const bool bound = lm == VRT_CUDA_LIST_REFERENCE_BOUND || lm == VRT_CUDA_LIST_BOUND;
+        if (lm != ctx->tiled_list_mode) return fail(ctx, VRT_CUDA_E_STATE, "list mode differs from the tiled frame");
+        if (tiled && ((int)frame->tiles_x != ctx->tiled_tiles_x || (int)frame->tiles_y != ctx->tiled_tiles_y))
+            return fail(ctx, VRT_CUDA_E_STATE, "tile count differs from the tiled frame");
+        if (bound && (frame->bound_sigmas > 0.f ? frame->bound_sigmas : 6.0f) != ctx->tiled_bound) return fail(ctx, VRT_CUDA_E_STATE, "bound_sigmas differs from the tiled frame");
+    }
     const uint32_t approx_erf = frame->flags & VRT_CUDA_APPROX_ERF_MASK, approx_exp = frame->flags & VRT_CUDA_APPROX_EXP_MASK;
     if ((approx_erf || approx_exp) && (frame->flags & VRT_CUDA_DEPTH_WINDOW))
         return fail(ctx, VRT_CUDA_E_INVALID, "the depth window needs a saturating odd erf: not available with VRT_CUDA_APPROX_*");
     if (approx_exp > VRT_CUDA_APPROX_EXP_SPLINE) return fail(ctx, VRT_CUDA_E_INVALID, "unknown exp approximation");
     RenderArgs a{};
+    a.geom = G;
     a.rec = (const Rec *)ctx->rec.p;
     a.list_off = (const uint32_t *)ctx->coffsets.p;
     a.list_idx = (G.list_kind == 2 || (ctx->lists_from_host && !ctx->literal)) ? nullptr : (const uint32_t *)ctx->cidx.p;
@@ -1069,7 +1232,16 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.radiance = (float4 *)radiance_dev;
     a.terms_exec = &((TileStats *)ctx->stats.p)->terms_exec;
     a.terms_sat = &((TileStats *)ctx->stats.p)->terms_sat;
-    a.window = ((frame->flags & VRT_CUDA_DEPTH_WINDOW) && a.list_idx != nullptr) ? 1u : 0u;
+    a.terms_term = &((TileStats *)ctx->stats.p)->terms_term;
+    a.scene_info = (const uint32_t *)ctx->scene_info.p;
+    a.abort_flag = ctx->abort_dev;
+    a.terminate = (frame->flags & VRT_CUDA_NO_TERMINATE) ? 0u : 1u;
+    // banded evaluation is the default wherever the lists are depth-sorted index lists (every bounded mode and the visible
+    // lists of the literal modes); VRT_CUDA_EVAL_ALL asks for every listed term, the approximation variants need it
+    const bool explicit_window = (frame->flags & VRT_CUDA_DEPTH_WINDOW) != 0;
+    if (explicit_window && (a.list_idx == nullptr || !ctx->lists_sorted))
+        return fail(ctx, VRT_CUDA_E_INVALID, "VRT_CUDA_DEPTH_WINDOW needs depth-sorted per-cell lists: not available on literally walked lists (VRT_CUDA_NO_SKIP)");
+    a.window = (a.list_idx != nullptr && ctx->lists_sorted && !(frame->flags & (VRT_CUDA_EVAL_ALL | VRT_CUDA_NO_SKIP)) && !approx_erf && !approx_exp) ? 1u : 0u;
     a.cell_slot = (const uint32_t *)ctx->cell_slot.p;
     if (ctx->n_split)
         if (int rc = reserve(ctx, ctx->partial, (size_t)ctx->n_split * 32 * sizeof(float4))) return rc;
@@ -1080,6 +1252,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.alpha_from_w = (frame->flags & VRT_CUDA_ALPHA_FROM_W) ? 1u : 0u;
     CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));
     CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_exec, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_term, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->render_launches = 1;
     int rc;
@@ -1099,29 +1272,14 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (stats)
-    {
-        TileStats ts;
-        CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        std::memset(stats, 0, sizeof(*stats));
-        stats->n_gaussians = ctx->n_gauss;
-        stats->n_cells = ctx->literal ? ctx->lit_n_lists : ctx->n_lists;
-        stats->list_entries = ctx->literal ? ctx->lit_stats.entries : ts.entries;
-        stats->max_list = (uint32_t)(ctx->literal ? ctx->lit_stats.max_list : ts.max_list);
-        stats->n_launches = ctx->launches + ctx->render_launches;
-        stats->terms_listed = ctx->literal ? ctx->lit_stats.terms_listed : ts.terms_listed;
-        stats->terms_executed = (double)ts.terms_exec;
-        stats->terms_saturated = (double)ts.terms_sat;
-        stats->ms_tile = ctx->ms_tile;
-        CU(cudaEventElapsedTime(&stats->ms_render, ctx->ev[2], ctx->ev[3]));
-        stats->ms_total = stats->ms_tile + stats->ms_render;
-        stats->slice = (uint32_t)G.slice;
-    }
+    if (stats) return read_stats(ctx, stats);
     return 0;
 }
 
-int vrt_cuda_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats)
+// running: optional pointer to the caller's `running` flag (the `const bool &running` of the reference's entries; one byte,
+// written by another thread).  While the frame is in flight the host polls it; when it goes false the mapped abort word is
+// raised, the persistent warps stop taking work items, and the call returns VRT_CUDA_INTERRUPTED with a partial image.
+static int render_host(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats, const volatile unsigned char *running)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
     if (!frame) return fail(ctx, VRT_CUDA_E_INVALID, "frame is NULL");
@@ -1131,14 +1289,49 @@ int vrt_cuda_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *im
         if (int rc = reserve(ctx, ctx->out_image, npix * sizeof(uint32_t))) return rc;
     if (radiance)
         if (int rc = reserve(ctx, ctx->out_rad, npix * sizeof(float) * 4)) return rc;
-    int rc = vrt_cuda_render_device(ctx, frame, image ? (uint32_t *)ctx->out_image.p : nullptr, radiance ? (float *)ctx->out_rad.p : nullptr, stats);
+    if (running && !*running) return VRT_CUDA_INTERRUPTED;
+    // with a `running` flag the statistics are read after the poll loop, not inside render_device (which would block)
+    int rc = vrt_cuda_render_device(ctx, frame, image ? (uint32_t *)ctx->out_image.p : nullptr, radiance ? (float *)ctx->out_rad.p : nullptr, running ? nullptr : stats);
     if (rc) return rc;
+    bool interrupted = false;
+    if (running)
+    {
+        while (cudaEventQuery(ctx->ev[3]) == cudaErrorNotReady)
+        {
+            if (!*running && !interrupted)
+            {
+                if (int ra = vrt_cuda_abort(ctx, 1)) return fail(ctx, ra, "vrt_cuda_abort failed");
+                interrupted = true;
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+        cudaGetLastError();
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (interrupted)
+            if (int ra = vrt_cuda_abort(ctx, 0)) return fail(ctx, ra, "vrt_cuda_abort failed");
+        if (stats)
+            if (int rs = read_stats(ctx, stats)) return rs;
+        if (interrupted) return VRT_CUDA_INTERRUPTED;
+    }
     const FrameGeom &G = ctx->geom;
     const size_t row0 = (size_t)G.row_begin, rows = (size_t)(G.row_end - G.row_begin);
+    if (image) pin_host(ctx, image + row0 * G.W, rows * G.W * sizeof(uint32_t));
+    if (radiance) pin_host(ctx, radiance + row0 * G.W * 4, rows * G.W * sizeof(float) * 4);
     if (image) CU(cudaMemcpyAsync(image + row0 * G.W, (uint32_t *)ctx->out_image.p + row0 * G.W, rows * G.W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (radiance) CU(cudaMemcpyAsync(radiance + row0 * G.W * 4, (float *)ctx->out_rad.p + row0 * G.W * 4, rows * G.W * sizeof(float) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int vrt_cuda_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats)
+{
+    return render_host(ctx, frame, image, radiance, stats, nullptr);
+}
+
+int vrt_cuda_render_interruptible(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats,
+                                  const volatile unsigned char *running)
+{
+    return render_host(ctx, frame, image, radiance, stats, running);
 }
 
 int vrt_cuda_frame_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance, vrt_cuda_stats *stats)

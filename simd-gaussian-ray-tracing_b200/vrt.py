@@ -24,7 +24,10 @@ LIST_REFERENCE, LIST_REFERENCE_BOUND, LIST_ALL, LIST_BOUND = 0 << 2, 1 << 2, 2 <
 QUANT_TRUNCATE, QUANT_NEAREST = 0 << 4, 1 << 4
 ALPHA_OPAQUE, ALPHA_FROM_W = 0 << 5, 1 << 5
 NO_SKIP = 1 << 6
-DEPTH_WINDOW = 1 << 7
+DEPTH_WINDOW = 1 << 7  # round-1 name of the (now default) banded evaluation
+EVAL_ALL = 1 << 12  # evaluate every listed term: no saturation shortcut, no early exit
+NO_TERMINATE = 1 << 13  # banded evaluation without the transmittance early exit
+INTERRUPTED = 1  # vrt_cuda_render_interruptible: `running` went false mid-frame
 # alternative approximations (src/vrt/approx.h:10-46) and the function ids of Renderer.approx_table
 APPROX_ERF_SPLINE, APPROX_ERF_SPLINE_MIRROR, APPROX_ERF_TAYLOR, APPROX_ERF_MASK = 1 << 8, 2 << 8, 3 << 8, 3 << 8
 APPROX_EXP_FAST, APPROX_EXP_SPLINE, APPROX_EXP_MASK = 1 << 10, 2 << 10, 3 << 10
@@ -187,6 +190,31 @@ class Renderer:
         self._check(self._lib.vrt_cuda_render(self._h, ctypes.byref(frame), _ptr(image) if image is not None else None,
                                               _ptr(radiance) if radiance is not None else None, ctypes.byref(st)), "vrt_cuda_render")
         return image, radiance, st.as_dict()
+
+    def render_interruptible(self, frame, running, want_image=True, want_radiance=False):
+        """vrt_cuda_render_interruptible: `running` is a one-byte numpy array (the reference's `const bool &running`) another
+        thread may clear.  -> (interrupted: bool, image | None, radiance | None, stats)."""
+        h, w = frame.height, frame.width
+        image = np.zeros((h, w), np.uint32) if want_image else None
+        radiance = np.zeros((h, w, 4), np.float32) if want_radiance else None
+        st = Stats()
+        rc = self._lib.vrt_cuda_render_interruptible(self._h, ctypes.byref(frame), _ptr(image) if image is not None else None,
+                                                     _ptr(radiance) if radiance is not None else None, ctypes.byref(st), _ptr(running))
+        if rc not in (0, INTERRUPTED):
+            self._check(rc, "vrt_cuda_render_interruptible")
+        return rc == INTERRUPTED, image, radiance, st.as_dict()
+
+    def abort(self, on=True):
+        self._check(self._lib.vrt_cuda_abort(self._h, int(bool(on))), "vrt_cuda_abort")
+
+    def set_host_pinning(self, on=True):
+        self._check(self._lib.vrt_cuda_set_host_pinning(self._h, int(bool(on))), "vrt_cuda_set_host_pinning")
+
+    def pin_buffer(self, array):
+        self._check(self._lib.vrt_cuda_pin_buffer(self._h, _ptr(array), array.nbytes), "vrt_cuda_pin_buffer")
+
+    def unpin_buffer(self, array):
+        self._check(self._lib.vrt_cuda_unpin_buffer(self._h, _ptr(array)), "vrt_cuda_unpin_buffer")
 
     def render_device(self, frame, image_ptr, radiance_ptr=0, want_stats=False):
         st = Stats() if want_stats else None

@@ -152,15 +152,12 @@ def translate(name, src):
         # The interpreter runs one kernel at a time on process-wide state and keeps ONE copy of the __constant__ frame geometry
         # (a GPU has one per device): every C-ABI entry that touches device state takes a process-wide recursive lock, so
         # host threads driving different contexts (the app's --gpus mode) serialise call by call.
-        entries = ("create|destroy|approx_table|sync|tile|set_tile_lists|get_lists|row_costs|render_device|render|frame_render|"
-                   "fp32_peak|approx_rate|term_peak|mix_peak")
+        entries = ("create|destroy|approx_table|sync|tile|set_tile_lists|get_lists|row_costs|render_device|frame_render|"
+                   "fp32_peak|approx_rate|term_peak|mix_peak|set_host_pinning|pin_buffer|unpin_buffer")
         src, k = re.subn(r"^((?:int|void) vrt_cuda_(?:" + entries + r")\([^;{]*\)\n\{\n)", r"\1    emu::ApiLock emu_api_lock_;\n", src, flags=re.M)
-        assert k == 15, f"{k} C-ABI entry definitions found for the interpreter's API lock (15 expected)"
-        src, k = re.subn(r"^(static int set_gaussians_impl\([^;{]*\)\n\{\n)", r"\1    emu::ApiLock emu_api_lock_;\n", src, flags=re.M)
-        assert k == 1
-    if name == "k2_window.cuh":
-        src, k = re.subn(r"extern\s+__shared__\s+__align__\(16\)\s+unsigned char s_raw\[\];", "unsigned char *s_raw = emu::dynamic_smem();", src)
-        assert k == 1, "dynamic shared memory declaration of k2_window not found"
+        assert k == 17, f"{k} C-ABI entry definitions found for the interpreter's API lock (17 expected)"
+        src, k = re.subn(r"^(static int (?:set_gaussians_impl|render_host)\([^;{]*\)\n\{\n)", r"\1    emu::ApiLock emu_api_lock_;\n", src, flags=re.M)
+        assert k == 2
     assert "<<<" not in src and not re.search(r"\basm\b", src), f"{name}: untranslated CUDA construct left"
     return src
 

@@ -99,7 +99,7 @@ struct ApiLock
     ApiLock();
     ~ApiLock();
 };
-enum { K_BALLOT = 1, K_ANY, K_ALL, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_REDUCE_MAX, K_REDUCE_MIN, K_SYNCWARP };
+enum { K_BALLOT = 1, K_ANY, K_ALL, K_SHFL, K_SHFL_XOR, K_SHFL_UP, K_SHFL_DOWN, K_REDUCE_MAX, K_REDUCE_MIN, K_SYNCWARP };
 } // namespace emu
 
 #define threadIdx (emu::cur().tid)
@@ -154,6 +154,14 @@ static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta)
     emu::warp_gather(mask, emu::bits(v), o, emu::K_SHFL_UP);
     const unsigned l = emu::lane_id();
     return l >= delta ? emu::unbits<T>(o[l - delta]) : v;
+}
+template <class T>
+static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta)
+{
+    uint64_t o[32];
+    emu::warp_gather(mask, emu::bits(v), o, emu::K_SHFL_DOWN);
+    const unsigned l = emu::lane_id();
+    return l + delta < 32 ? emu::unbits<T>(o[l + delta]) : v;
 }
 static inline int __reduce_max_sync(unsigned mask, int v)
 {
@@ -228,6 +236,14 @@ static inline T atomicMax(T *p, U v)
     return old;
 }
 
+template <class T, class U>
+static inline T atomicOr(T *p, U v)
+{
+    const T old = *p;
+    *p = old | (T)v;
+    return old;
+}
+
 // ---- the slice of the runtime API the product uses --------------------------------------------------------------------------
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
@@ -259,6 +275,19 @@ cudaError_t cudaEventCreate(cudaEvent_t *e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
+// mapped / registered host memory: host and "device" share one address space here, so these are bookkeeping only
+enum { cudaErrorNotReady = 600 };
+enum { cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0, cudaHostRegisterPortable = 1 };
+static inline cudaError_t cudaMemset(void *p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; };
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = std::calloc(1, n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return cudaSuccess; }
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; } // kernels complete inside their launch
 template <class T>
 static inline cudaError_t cudaMemcpyToSymbolAsync(T &symbol, const void *src, size_t n, size_t offset, cudaMemcpyKind, cudaStream_t)
 {

@@ -50,8 +50,9 @@ def run_case(pkg, renderer, rng, verbose=False):
     bounded = kind in ("bound", "reference_bound")
     if not bounded and rng.integers(0, 3) == 0:
         flags |= V.NO_SKIP
-    if bounded and rng.integers(0, 2) == 0:
-        flags |= V.DEPTH_WINDOW
+    if not (flags & V.NO_SKIP):  # the banded kernel is the default: half of the cases ask for the full evaluation instead
+        pick = int(rng.integers(0, 4))
+        flags |= (V.EVAL_ALL, V.EVAL_ALL, 0, V.NO_TERMINATE)[pick]
     rows = (0, 0)
     if rng.integers(0, 2) == 0 and H > 1:
         a = int(rng.integers(0, H - 1))

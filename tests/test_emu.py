@@ -230,7 +230,7 @@ def test_multi_rank_protocol_with_rendering(build_emu, world, tmp_path):
     assert len(bounds) == world + 1 and bounds[0] == "0" and bounds[-1] == "96"
 
 
-@pytest.mark.parametrize("extra", [[], ["--lists", "reference", "--slice", "16", "--no-cpu-baseline"]])
+@pytest.mark.parametrize("extra", [[], ["--lists", "reference", "--slice", "16", "--no-cpu-baseline", "--only"]])
 def test_bench_cuda_arm_contract(build_emu, extra):
     """bench.py's own arm cannot run without a GPU, so its control flow and the JSON line the driver parses are exercised here
     with the interpreter standing in for the device and host tensors for torch's device tensors
@@ -239,7 +239,7 @@ def test_bench_cuda_arm_contract(build_emu, extra):
     import json
 
     build_emu.build()
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_bench_emulated.py"), "--config", "1", "--steps", "2", "--warmup", "3", *extra], cwd=ROOT,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "run_bench_emulated.py"), "--config", "1", "--configs", "0", "--steps", "2", "--warmup", "3", *extra], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -252,27 +252,34 @@ def test_bench_cuda_arm_contract(build_emu, extra):
     assert d["steps"] == 2 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
     cfg = d["config"]
     assert cfg["workload"].startswith("config1") and "model" not in cfg and cfg["bands"] == [0, 256]
-    assert 0 < cfg["terms_executed_per_frame"] <= cfg["terms_listed_per_frame"]
-    # value = executed terms / time of the timed steps
-    assert abs(d["value"] - cfg["terms_executed_per_frame"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    assert 0 < cfg["terms_evaluated_per_frame"] <= cfg["terms_resolved_per_frame"] <= cfg["terms_listed_per_frame"]
+    assert abs(cfg["terms_resolved_per_frame"] - (cfg["terms_evaluated_per_frame"] + cfg["terms_saturated_per_frame"] + cfg["terms_terminated_per_frame"])) <= 1e-9 * cfg["terms_resolved_per_frame"]
+    # value = resolved terms / time of the timed steps; the strict figure counts the evaluated ones only
+    assert abs(d["value"] - cfg["terms_resolved_per_frame"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    assert abs(d["strict_evals_per_s"] - cfg["terms_evaluated_per_frame"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
     e2e = d["e2e"]
     assert e2e["unit"] == d["unit"] and e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 16 * 40 and e2e["d2h_bytes_per_step"] == 256 * 256 * 4
+    assert "vrt_cuda_render(host image)" in e2e["path"] and d["e2e_pageable"]["value"] > 0  # N = 1: the reference-facing host-buffer call
     assert d["gpu_launches"] > 0
     roof = d["roofline"]
-    assert roof["bound"] == "fp32" and roof["kernel"] == "k2_render" and roof["unit"] == "TFLOP/s" and roof["flops_per_term"] == 15.0
+    assert roof["bound"] == "fp32" and roof["kernel"] == "k2_band" and roof["unit"] == "TFLOP/s" and roof["flops_per_term"] == 15.0
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) <= 1e-9
     assert abs(roof["achieved"] - roof["terms_per_launch"] * 15.0 / (roof["ms_per_launch"] * 1e-3) / 1e12) <= 1e-6 * roof["achieved"]
-    pm = roof["pipe_model"]
+    strict = cfg["strict_mode"]
+    sroof = strict["roofline"]
+    assert sroof["kernel"] == "k2_render" and strict["ms_per_step"] > 0 and strict["terms_evaluated_per_frame"] >= cfg["terms_evaluated_per_frame"]
+    pm = sroof["pipe_model"]
     assert pm["ceiling_terms_per_s"] == 2 * 4 * 32 / 8.0 * 1965e6 and 0 < pm["frac_of_ceiling"] < 1  # 2 pretend SMs at the B200's max clock
-    assert abs(pm["frac_of_ceiling"] / roof["frac"] - roof["peak"] * 1e12 / 15.0 / pm["ceiling_terms_per_s"]) <= 1e-9
+    assert abs(pm["frac_of_ceiling"] / sroof["frac"] - sroof["peak"] * 1e12 / 15.0 / pm["ceiling_terms_per_s"]) <= 1e-9
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     if extra:
-        assert "cpu_baseline" not in d and cfg["slice"] == 16 and cfg["depth_window_mode"] is None and "literal" in cfg["lists"]
+        assert "cpu_baseline" not in d and cfg["slice"] == 16 and "literal" in cfg["lists"] and "configs" not in d
         assert cfg["terms_listed_per_frame"] == 256 * 256 * 5 * 81  # the reference's own lists: 9 Gaussians in every tile
     else:
         cb = d["cpu_baseline"]
         assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == "evals/s" and cb["sample"]
-        assert cfg["depth_window_mode"]["ms_per_step"] > 0
+        assert d["parity_vs_reference"] is None or d["parity_vs_reference"]["max_channel_lsb"] <= 1  # config 1 is well conditioned
+        assert set(d["configs"]) == {"0", "1"} and d["configs"]["0"]["ms_per_frame"] > 0 and d["configs"]["0"]["roofline_frac"] > 0
 
 
 def test_bench_cuda_arm_two_ranks(build_emu):
@@ -285,7 +292,7 @@ def test_bench_cuda_arm_two_ranks(build_emu):
     build_emu.build()
     env = dict(os.environ, VRT_EMU_DEVICES="2")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-                        os.path.join(ROOT, "tests", "emu", "run_bench_emulated.py"), "--gpus", "2", "--config", "1", "--steps", "2", "--warmup", "3"], cwd=ROOT, env=env,
+                        os.path.join(ROOT, "tests", "emu", "run_bench_emulated.py"), "--gpus", "2", "--config", "1", "--configs", "0", "--steps", "2", "--warmup", "3"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -295,5 +302,5 @@ def test_bench_cuda_arm_two_ranks(build_emu):
     assert d["n_gpus"] == 2 and d["scaling"] == "strong" and "cpu_baseline" not in d
     assert len(cfg["bands"]) == 3 and cfg["bands"][0] == 0 and cfg["bands"][-1] == 256 and all(b % 16 == 0 for b in cfg["bands"])
     assert cfg["gathered_image_equals_single_gpu_frame"] is True
-    assert len(cfg["per_rank"]["ms_render"]) == 2 and abs(sum(cfg["per_rank"]["terms_executed"]) - cfg["terms_executed_per_frame"]) <= 1e-9 * cfg["terms_executed_per_frame"]
+    assert len(cfg["per_rank"]["ms_render"]) == 2 and abs(sum(cfg["per_rank"]["terms_executed"]) - cfg["terms_evaluated_per_frame"]) <= 1e-9 * cfg["terms_evaluated_per_frame"]
     assert d["e2e"]["value"] > 0 and d["roofline"]["frac"] > 0

@@ -396,32 +396,109 @@ def test_bounded_lists_are_conservative_and_tight(pkg, renderer):
 
 @pytest.mark.parametrize("erf", [0, 1])
 def test_depth_window_mode_is_the_same_image(pkg, renderer, erf):
-    """VRT_CUDA_DEPTH_WINDOW: depth-sorted lists + the saturation shortcut must reproduce the plain evaluation (only the order
-    of the fp32 sums changes) while evaluating far fewer terms; every listed term is either evaluated or resolved."""
+    """The banded default (depth-sorted lists + the saturation shortcut + the early exit) must reproduce the evaluation of
+    every term (VRT_CUDA_EVAL_ALL; only the order of the fp32 sums changes) while evaluating far fewer terms; every listed
+    term is evaluated, resolved by saturation or dropped by the early exit."""
     V = pkg.vrt
     W = 512
     scene = pkg.scenes.synthetic(60000, 21, -2.3, -1.7)
     cam, origin = V.camera_t.app(W, W, rotation=12.0)
     renderer.set_gaussians(scene)
     base_flags = ((V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND) & ~1 | erf
-    f0 = renderer.frame(cam.view_matrix, origin, W, W, base_flags, (32, 32), 6.0)
+    f0 = renderer.frame(cam.view_matrix, origin, W, W, base_flags | V.EVAL_ALL, (32, 32), 6.0)
     img0, rad0, st0 = renderer.frame_render(f0, True, True)
-    f1 = renderer.frame(cam.view_matrix, origin, W, W, base_flags | V.DEPTH_WINDOW, (32, 32), 6.0)
+    f1 = renderer.frame(cam.view_matrix, origin, W, W, base_flags, (32, 32), 6.0)
     img1, rad1, st1 = renderer.frame_render(f1, True, True)
     d = float(np.abs(rad0 - rad1).max())
-    print(f"erf {erf}: plain {st0['terms_executed']:.3e} terms in {st0['ms_render']:.2f} ms; window {st1['terms_executed']:.3e} evaluated + "
-          f"{st1['terms_saturated']:.3e} saturated in {st1['ms_render']:.2f} ms; max |diff| {d:.2e}")
+    print(f"erf {erf}: every term {st0['terms_executed']:.3e} in {st0['ms_render']:.2f} ms; banded {st1['terms_executed']:.3e} evaluated + "
+          f"{st1['terms_saturated']:.3e} saturated + {st1['terms_terminated']:.3e} terminated in {st1['ms_render']:.2f} ms; max |diff| {d:.2e}")
     assert d <= 2e-5  # the saturated part enters as one large partial sum: fp32 reassociation ~ sum(A) * 2^-23
     assert channel_diff_lsb(img0, img1) <= 1
     assert st1["terms_listed"] == st0["terms_listed"]
     # (emitter blocks group different emitters once the list is depth-sorted, so the warp-uniform skips differ marginally)
-    assert abs(st1["terms_executed"] + st1["terms_saturated"] - st0["terms_executed"]) <= 1e-2 * st0["terms_executed"]
-    assert st1["terms_executed"] < 0.5 * st0["terms_executed"]
-    assert st0["terms_saturated"] == 0
+    assert abs(st1["terms_executed"] + st1["terms_saturated"] + st1["terms_terminated"] - st0["terms_executed"]) <= 1e-2 * st0["terms_executed"]
+    assert st1["terms_executed"] < 0.3 * st0["terms_executed"]
+    assert st0["terms_saturated"] == 0 and st0["terms_terminated"] == 0
     # and against the arbiter
     pix = all_pixels(W, W, 997)
     ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1 - erf, f64="unit", near_sigmas=12)
     check(gpu_at(rad1, pix, W), ideal, f"depth-window mode vs arbiter (erf {erf})")
+
+
+def test_two_contexts_render_concurrently_on_one_device(pkg, renderer):
+    """The frame geometry is a kernel argument and the lists live in the context: two contexts on ONE GPU can have frames in
+    flight at the same time (the reference's entries are re-entrant).  Context B tiles and renders another camera and size
+    between A's tile and A's render, on its own stream, while A's frame is still enqueued; both must equal their solo frames."""
+    import torch
+
+    V = pkg.vrt
+    scene_a = np.load(os.path.join(GOLDEN, "monkey_gaussians.npy"))
+    scene_b = pkg.scenes.synthetic(20000, 3, -2.0, -1.5)
+    cam_a, origin_a = V.camera_t.app(256, 256)
+    cam_b, origin_b = V.camera_t.app(384, 192, rotation=25.0)
+    flags = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+    fa = renderer.frame(cam_a.view_matrix, origin_a, 256, 256, flags, (16, 16))
+    fb = renderer.frame(cam_b.view_matrix, origin_b, 384, 192, flags, (24, 12))
+    other = V.Renderer(renderer.device)
+    try:
+        renderer.set_gaussians(scene_a)
+        solo_a, _, _ = renderer.frame_render(fa, True, False)
+        other.set_gaussians(scene_b)
+        solo_b, _, _ = other.frame_render(fb, True, False)
+        img_a = torch.zeros((256, 256), dtype=torch.int32, device="cuda")
+        img_b = torch.zeros((192, 384), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(3):
+            renderer.tile(fa)
+            other.tile(fb)  # B's geometry is in flight between A's tile and A's render
+            renderer.render_device(fa, img_a.data_ptr(), 0)  # asynchronous: no stats
+            other.render_device(fb, img_b.data_ptr(), 0)
+            renderer.render_device(fa, img_a.data_ptr(), 0)
+        renderer.sync()
+        other.sync()
+        assert np.array_equal(img_a.cpu().numpy().view(np.uint32), solo_a)
+        assert np.array_equal(img_b.cpu().numpy().view(np.uint32), solo_b)
+    finally:
+        other.close()
+
+
+def test_interrupted_render_returns_early(pkg, renderer):
+    """`running` going false mid-frame (rt.h:244-246, 289, 334, 382; main.cpp:244): the host poll raises the mapped abort word,
+    the persistent warps stop taking work, and the call reports the interruption long before the frame would have finished.
+    The literal tile lists of the teapot without culling take ~0.8 s at 512^2 on a B200, so a flag cleared after 30 ms lands mid-frame."""
+    import threading
+    import time
+
+    V = pkg.vrt
+    scene = np.load(os.path.join(GOLDEN, "teapot_gaussians.npy"))
+    W = 512
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    f = renderer.frame(cam.view_matrix, origin, W, W, V.MODE8 | V.NO_SKIP, (16, 16))
+    renderer.tile(f)
+    running = np.ones(1, np.uint8)
+    t0 = time.time()
+    interrupted, _, _, st_full = renderer.render_interruptible(f, running, True, False)
+    full_s = time.time() - t0
+    assert not interrupted and st_full["terms_executed"] == st_full["terms_listed"]
+
+    def stop():
+        time.sleep(min(0.03, full_s / 4))
+        running[0] = 0
+
+    th = threading.Thread(target=stop)
+    t0 = time.time()
+    th.start()
+    interrupted, _, _, st = renderer.render_interruptible(f, running, True, False)
+    cut_s = time.time() - t0
+    th.join()
+    print(f"full frame {full_s * 1e3:.1f} ms ({st_full['terms_executed']:.3e} terms); interrupted after {cut_s * 1e3:.1f} ms with {st['terms_executed']:.3e} terms done")
+    assert interrupted and st["terms_executed"] < st_full["terms_executed"] and cut_s < 0.7 * full_s
+    # a flag that is already false returns at once, and the context renders normally afterwards
+    assert renderer.render_interruptible(f, running, True, False)[0]
+    running[0] = 1
+    interrupted, img, _, st2 = renderer.render_interruptible(f, running, True, False)
+    assert not interrupted and st2["terms_executed"] == st_full["terms_executed"]
 
 
 def test_errors_are_reported(pkg, renderer):
@@ -440,6 +517,19 @@ def test_errors_are_reported(pkg, renderer):
     cam2, origin2 = V.camera_t.app(96, 96, rotation=10.0)
     with pytest.raises(V.VrtCudaError):
         renderer.render(renderer.frame(cam2.view_matrix, origin2, 96, 96, V.MODE8, (4, 4)))  # camera moved: lists are stale
+    # the lists belong to one list mode, tile count and bound: a frame naming another one is refused, not rendered
+    with pytest.raises(V.VrtCudaError, match="list mode"):
+        renderer.render(renderer.frame(cam.view_matrix, origin, 96, 96, (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (4, 4)))
+    with pytest.raises(V.VrtCudaError, match="tile count"):
+        renderer.render(renderer.frame(cam.view_matrix, origin, 96, 96, V.MODE8, (8, 8)))
+    fb = renderer.frame(cam.view_matrix, origin, 96, 96, (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (4, 4), 6.0)
+    renderer.tile(fb)
+    with pytest.raises(V.VrtCudaError, match="bound_sigmas"):
+        renderer.render(renderer.frame(cam.view_matrix, origin, 96, 96, (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND, (4, 4), 8.0))
+    with pytest.raises(V.VrtCudaError, match="DEPTH_WINDOW"):  # literally walked lists cannot take the banded kernel
+        fl = renderer.frame(cam.view_matrix, origin, 96, 96, V.MODE4 | V.NO_SKIP | V.DEPTH_WINDOW)
+        renderer.tile(fl)
+        renderer.render(fl)
 
 
 def test_empty_scene_and_ragged_image(pkg, renderer):
@@ -501,6 +591,15 @@ def _full_size_case(pkg, renderer, scene, W, tiles, n_pix, seed):
     tile_px = W // tiles
     ideal = np.zeros((len(pix), 4))
     ref32 = np.zeros((len(pix), 4), np.float32)
+    # the COMPILED reference (oracle/_ref: radiance<transmittance<expf, abramowitz_stegun_erf>>, rt.h:146-164) on the same pixels and
+    # lists, fed (i) the directions its own normalize produces and (ii) the same directions rounded the IEEE way (<= 0.5 ulp
+    # apart): the difference between (i) and (ii) is the reference's own reproducibility on this scene
+    have_ref = Ref.available()
+    refc = np.zeros((len(pix), 4), np.float32)
+    refc_alt = np.zeros((len(pix), 4), np.float32)
+    d64 = dirs.astype(np.float64)
+    d64[:, :3] /= np.linalg.norm(d64[:, :3], axis=1, keepdims=True)
+    dirs_alt = d64.astype(np.float32)
     for k, p in enumerate(pix):
         row, col = int(p) // W, int(p) % W
         near = np.nonzero(cpu_lists.ray_distance_sigmas(scene, origin, dirs[k : k + 1])[:, 0] < 12.0)[0]
@@ -509,6 +608,9 @@ def _full_size_case(pkg, renderer, scene, W, tiles, n_pix, seed):
         if len(lst):
             ideal[k] = Oracle.radiance(lst, origin, dirs[k : k + 1], 1, "unit")[0]
             ref32[k] = Oracle.radiance(lst, origin, dirs[k : k + 1], 1)[0]
+            if have_ref:
+                refc[k] = Ref.radiance(lst, origin, dirs[k : k + 1], 1)[0]
+                refc_alt[k] = Ref.radiance(lst, origin, dirs_alt[k : k + 1], 1)[0]
     got = gpu_at(rad, pix, W)
     err = check(got, ideal, f"{len(scene)} Gaussians @{W}^2 vs arbiter")
     err_ref = float(np.abs(ref32 - ideal).max())
@@ -516,6 +618,15 @@ def _full_size_case(pkg, renderer, scene, W, tiles, n_pix, seed):
           f"tile {st['ms_tile']:.2f} ms, render {st['ms_render']:.2f} ms, max list {st['max_list']}")
     # framebuffer: the packed pixel equals the mode-8 packing of the radiance the kernel produced (K3 is exact integer work)
     assert np.array_equal(img, pack_image(rad, True, True))
+    if have_ref:
+        mx = lambda a, b: float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+        cuda_vs_ref, ref_spread, ref_vs_arbiter = mx(got, refc), mx(refc, refc_alt), mx(refc, ideal)
+        print(f"compiled reference: |CUDA - ref| {cuda_vs_ref:.3e}; |ref(dirs) - ref(dirs rounded once more)| {ref_spread:.3e}; |ref - arbiter| {ref_vs_arbiter:.3e}; "
+              f"|CUDA - arbiter| {err:.3e}")
+        # The north star's tolerance against "the reference's scalar path" can only be as tight as that path agrees with itself:
+        # the CUDA frame must be within max(1e-3, the reference's own spread under a half-ulp change of its ray directions) of it
+        assert cuda_vs_ref <= max(TOL_ABS, 1.5 * ref_spread), (cuda_vs_ref, ref_spread)
+        st = dict(st, cuda_vs_ref=cuda_vs_ref, ref_spread=ref_spread, ref_vs_arbiter=ref_vs_arbiter)
     return err, err_ref, st
 
 
@@ -523,12 +634,18 @@ def test_config4_full_size(pkg, renderer):
     err, err_ref, st = _full_size_case(pkg, renderer, pkg.scenes.config4(), 4096, 256, 160, 4)
     assert err <= 1e-4
     assert st["terms_executed"] <= st["terms_listed"]
+    if "ref_spread" in st:
+        # the compiled reference moves by more than the 1e-3 tolerance when its ray directions change by half an ulp
+        # (tests/golden/ref_self_spread.json, measured with oracle/_ref on this very sample): that is why the arbiter decides here
+        assert st["ref_spread"] > 1e-3 and st["ref_vs_arbiter"] > 10 * err
 
 
 def test_config5_full_size(pkg, renderer):
     err, err_ref, st = _full_size_case(pkg, renderer, pkg.scenes.config5(), 4096, 256, 160, 5)
     assert err <= 1e-4
     assert err_ref > err  # the reference's own fp32 evaluation is farther from the arbiter
+    if "ref_spread" in st:
+        assert st["ref_spread"] > 1e-3 and st["ref_vs_arbiter"] > 10 * err
 
 
 def test_config2_teapot_1024(pkg, renderer):

@@ -23,38 +23,79 @@ def bound_flags(V, erf=0):
 
 @pytest.mark.parametrize("erf", [0, 1])
 def test_depth_window_small(pkg, renderer, erf):
-    """Depth-window mode reproduces the plain evaluation and resolves most terms by saturation (k2_window)."""
+    """The banded default (k2_band) reproduces the evaluation of every term (VRT_CUDA_EVAL_ALL) and resolves most terms by
+    saturation; every listed term is evaluated, saturated or dropped by the early exit."""
     V = pkg.vrt
     W = 96
     scene = pkg.scenes.synthetic(2500, 21, -1.9, -1.4)
     cam, origin = V.camera_t.app(W, W, rotation=12.0)
     renderer.set_gaussians(scene)
-    f0 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf), (12, 12), 6.0)
+    f0 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf) | V.EVAL_ALL, (12, 12), 6.0)
     img0, rad0, st0 = renderer.frame_render(f0, True, True)
-    f1 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf) | V.DEPTH_WINDOW, (12, 12), 6.0)
+    f1 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf), (12, 12), 6.0)
     img1, rad1, st1 = renderer.frame_render(f1, True, True)
     assert float(np.abs(rad0 - rad1).max()) <= 2e-5
     assert channel_diff_lsb(img0, img1) <= 1
-    assert st1["terms_listed"] == st0["terms_listed"] and st0["terms_saturated"] == 0
-    assert abs(st1["terms_executed"] + st1["terms_saturated"] - st0["terms_executed"]) <= 1e-2 * st0["terms_executed"]
+    assert st1["terms_listed"] == st0["terms_listed"] and st0["terms_saturated"] == 0 and st0["terms_terminated"] == 0
+    resolved = st1["terms_executed"] + st1["terms_saturated"] + st1["terms_terminated"]
+    assert abs(resolved - st0["terms_executed"]) <= 1e-2 * st0["terms_executed"]
     assert 0 < st1["terms_saturated"] and st1["terms_executed"] < st0["terms_executed"]
+    # the explicit round-1 flag is the same path; without the early exit the image may differ by at most its eps per channel
+    f2 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V, erf) | V.DEPTH_WINDOW | V.NO_TERMINATE, (12, 12), 6.0)
+    _, rad2, st2 = renderer.frame_render(f2, False, True)
+    assert st2["terms_terminated"] == 0 and float(np.abs(rad2 - rad1).max()) <= 2e-6
     pix = all_pixels(W, W, 53)
     ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1 - erf, f64="unit", near_sigmas=12)
     check(gpu_at(rad1, pix, W), ideal, f"depth-window mode vs arbiter (erf {erf})")
 
 
+def test_early_exit_on_an_opaque_scene(pkg, renderer):
+    """Transmittance early exit (north_star subsystem 2): behind an opaque layer T is below eps for every pixel of
+    a cell, the warp breaks out of the emitter loop, and the image changes by less than the stated bound (1e-6 per channel)
+    against the same kernel without the exit -- and stays within tolerance of the arbiter.  A negative magnitude makes
+    T non-monotone: K0 flags the scene and the exit must stay off."""
+    V = pkg.vrt
+    W = 64
+    scene = pkg.scenes.synthetic(700, 33, -0.8, -0.5)  # sigma ~1-2 pixels at this size: every pixel is covered several times
+    scene[:, 9] *= 25.0  # optical depth 5 .. 37 through every Gaussian's centre: the cloud is opaque after a few of them
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    f_exit = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V), (8, 8), 6.0)
+    f_full = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V) | V.NO_TERMINATE, (8, 8), 6.0)
+    f_all = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V) | V.EVAL_ALL, (8, 8), 6.0)
+    _, rad_exit, st_exit = renderer.frame_render(f_exit, False, True)
+    _, rad_full, st_full = renderer.frame_render(f_full, False, True)
+    _, rad_all, st_all = renderer.frame_render(f_all, False, True)
+    print(f"evaluated {st_exit['terms_executed']:.3e} + saturated {st_exit['terms_saturated']:.3e} + terminated {st_exit['terms_terminated']:.3e} "
+          f"of {st_exit['terms_listed']:.3e}; without the exit {st_full['terms_executed']:.3e} evaluated")
+    assert st_exit["terms_terminated"] > 0.03 * st_exit["terms_listed"] and st_full["terms_terminated"] == 0
+    assert st_exit["terms_executed"] < st_full["terms_executed"]
+    assert float(np.abs(rad_exit - rad_full).max()) <= 1e-6 + 1e-6 * float(np.abs(rad_full).max())
+    # (optical depths of several hundred per pixel: the two evaluation orders differ by sum(A) * 2^-23 in ln T)
+    assert float(np.abs(rad_exit - rad_all).max()) <= 1e-4 * max(1.0, float(rad_all.max()))
+    pix = all_pixels(W, W, 29)
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1, f64="unit", near_sigmas=12)
+    check(gpu_at(rad_exit, pix, W), ideal, "early exit vs arbiter")
+    # one absorbing-negative Gaussian: no early exit anywhere in the frame
+    bad = scene.copy()
+    bad[7, 9] = -1.0
+    renderer.set_gaussians(bad)
+    _, _, st_bad = renderer.frame_render(f_exit, False, True)
+    assert st_bad["terms_terminated"] == 0
+
+
 def test_depth_window_long_lists_take_the_in_loop_test(pkg, renderer):
-    """Lists longer than the window kernel's per-warp cache (160 entries) go to k2_render's in-loop saturation test; a frame
-    that mixes both kinds must still be the plain image."""
+    """Lists longer than the banded kernel's per-warp cache (160 entries) go to k2_render's in-loop saturation test; a frame
+    that mixes both kinds must still be the image of the full evaluation."""
     V = pkg.vrt
     W = 32
     scene = pkg.scenes.synthetic(2000, 9, -1.0, -0.7)  # wide Gaussians: every cell lists hundreds
     cam, origin = V.camera_t.app(W, W)
     renderer.set_gaussians(scene)
-    f0 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V), (4, 4), 6.0)
+    f0 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V) | V.EVAL_ALL, (4, 4), 6.0)
     _, rad0, st0 = renderer.frame_render(f0, False, True)
     assert st0["max_list"] > 160
-    f1 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V) | V.DEPTH_WINDOW, (4, 4), 6.0)
+    f1 = renderer.frame(cam.view_matrix, origin, W, W, bound_flags(V), (4, 4), 6.0)
     _, rad1, st1 = renderer.frame_render(f1, False, True)
     assert float(np.abs(rad0 - rad1).max()) <= 1e-4 * max(1.0, float(rad0.max()))
     assert st1["terms_saturated"] > 0
