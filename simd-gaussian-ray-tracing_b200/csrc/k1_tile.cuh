@@ -1,4 +1,5 @@
-// k1_tile.cuh -- K0 (per-Gaussian frame records) and K1 (multi-level culling, scans, depth sort, cost histogram, work queue).
+// k1_tile.cuh -- K0 (per-Gaussian frame records), the culling predicate, the literal per-tile lists, scans, cost histogram and work queue
+// (the bounded per-cell lists are built by k1_bin.cuh).
 // A fragment of vrt_cuda.cu: included there, in this order, inside its anonymous namespace.  Not a stand-alone header.
 #pragma once
 
@@ -160,103 +161,6 @@ __device__ __forceinline__ bool cull_test(const FrameGeom &G, const CullRect &rc
     return true;
 }
 
-// One culling level.  The cell grid is grouped into gx x gy-cell groups (ngx x ngy of them); every group scans the list of
-// the coarser group that contains it (pgx x pgy cells, pngx per row) and keeps what passes its own test.  The root level
-// has no parent: it scans the scene itself in n_seg segments of ROOT_SEG Gaussians, one warp per (group, segment), and the
-// per-segment pieces concatenate in index order.  The finest level has gx = gy = 1 (one 8x4-pixel cell per warp).
-struct CullLevel
-{
-    int gx, gy, ngx, ngy;
-    int pgx, pgy, pngx;
-    int is_root, n_seg;
-};
-
-// WRITE = false: counts[group * n_seg + seg] ; WRITE = true: indices at offsets[group * n_seg + seg].
-// 32 candidates per step, one per lane: predicate -> ballot -> popc of the lower lanes = ordered slot (lists keep
-// ascending Gaussian index, so K2's sums are reproducible).
-template <bool WRITE>
-__global__ void __launch_bounds__(256) k1_cull(const FrameGeom G, const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root, const CullLevel L,
-                                               const uint32_t *__restrict__ parent_off, const uint32_t *__restrict__ parent_idx,
-                                               uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets, uint32_t *__restrict__ out_idx,
-                                               uint32_t n_work)
-{
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= n_work) return;
-    const uint32_t group = wid / L.n_seg, seg = wid % L.n_seg;
-    const int gxi = group % L.ngx, gyi = group / L.ngx;
-    // pixel rect of the group = union of its cells' rects
-    const int cx0 = gxi * L.gx, cx1 = min(G.ncx, cx0 + L.gx) - 1;
-    const int cy0 = gyi * L.gy, cy1 = min(G.ncy, cy0 + L.gy) - 1;
-    int x0, y0, x1, y1;
-    if (G.uniform)
-    {
-        x0 = cx0 * CELL_W; y0 = cy0 * CELL_H;
-        x1 = (cx1 + 1) * CELL_W; y1 = (cy1 + 1) * CELL_H;
-    }
-    else
-    {
-        // ragged tiles (tile size not a multiple of the cell): cells restart at every tile edge
-        x0 = (cx0 / G.cptx) * G.tile_w + (cx0 % G.cptx) * CELL_W;
-        y0 = (cy0 / G.cpty) * G.tile_h + (cy0 % G.cpty) * CELL_H;
-        x1 = min((cx1 / G.cptx) * G.tile_w + min(G.tile_w, (cx1 % G.cptx + 1) * CELL_W), G.W);
-        y1 = min((cy1 / G.cpty) * G.tile_h + min(G.tile_h, (cy1 % G.cpty + 1) * CELL_H), G.H);
-    }
-    uint32_t begin, end;
-    if (L.is_root)
-    {
-        begin = seg * ROOT_SEG;
-        end = min(n_root, begin + ROOT_SEG);
-    }
-    else
-    {
-        // the parent's list, cut into n_seg pieces of whole 32-entry steps (coarse levels have few groups and long parent
-        // lists: one warp per group would leave most SMs idle behind a serial scan)
-        const uint32_t parent = (uint32_t)((cy0 / L.pgy) * L.pngx + (cx0 / L.pgx));
-        const uint32_t pb = parent_off[parent], pe = parent_off[parent + 1];
-        const uint32_t per = (((pe - pb) + L.n_seg - 1) / L.n_seg + 31u) & ~31u;
-        begin = min(pe, pb + seg * per);
-        end = min(pe, begin + per);
-    }
-    // groups outside the rendered row band get empty lists
-    const bool in_band = y1 > G.row_begin && y0 < G.row_end;
-    uint32_t base = WRITE ? offsets[wid] : 0u;
-    uint32_t count = 0;
-    if (in_band && end > begin)
-    {
-        CullRect rc;
-        make_rect(G, x0, x1, y0, y1, rc);
-        for (uint32_t k = begin; k < end; k += 32)
-        {
-            const uint32_t e = k + lane;
-            bool pass = false;
-            uint32_t gi = 0;
-            if (e < end)
-            {
-                gi = (L.is_root || parent_idx == nullptr) ? e : parent_idx[e]; // no index array: the parent list is a contiguous range
-                const float4 a = cullrec[2 * gi]; // (oc.xyz, sigma)
-                const float4 cr = G.use_ref ? cullrec[2 * gi + 1] : make_float4(0.f, 0.f, 0.f, 1.f);
-                pass = cull_test(G, rc, a, a.w, cr);
-            }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-            if (WRITE)
-            {
-                if (pass) out_idx[base + __popc(ballot & ((1u << lane) - 1u))] = gi;
-                base += __popc(ballot);
-            }
-            else count += __popc(ballot);
-        }
-    }
-    if (!WRITE && lane == 0) counts[wid] = count;
-}
-
-// offsets of a segmented root level -> one offset per group (+ the total)
-__global__ void k1_group_offsets(const uint32_t *__restrict__ seg_offsets, uint32_t *__restrict__ group_offsets, uint32_t n_groups, int n_seg)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n_groups) group_offsets[i] = seg_offsets[(size_t)i * n_seg];
-}
-
 // pure REFERENCE lists (one list per reference tile), level 1 with children = tiles
 template <bool WRITE>
 __global__ void __launch_bounds__(256) k1_cull_tiles(const FrameGeom G, const Rec *__restrict__ rec, const float4 *__restrict__ cullrec, uint32_t n_root,
@@ -301,74 +205,7 @@ __global__ void __launch_bounds__(256) k1_cull_tiles(const FrameGeom G, const Re
     if (!WRITE && threadIdx.x == 0) counts[tile] = s_base;
 }
 
-// Depth order for the depth-window mode: every cell's index list is sorted by the depth of the centre along the cell's
-// centre ray (ties by Gaussian index, so the order is deterministic).  One warp per cell, bitonic network in shared memory;
-// lists longer than SORT_CAP stay in index order (the window test is valid for any order, it just saturates less often).
-constexpr int SORT_CAP = 512;
 __device__ __forceinline__ void cell_rect(const FrameGeom &G, int cx, int cy, int &x0, int &y0, int &w, int &h);
-__global__ void __launch_bounds__(128) k1_sort_cells(const FrameGeom G, const float4 *__restrict__ cullrec, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ list_idx,
-                                                     uint32_t n_cells)
-{
-    __shared__ float s_key[4][SORT_CAP];
-    __shared__ uint32_t s_val[4][SORT_CAP];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t cell = blockIdx.x * 4 + w;
-    if (cell >= n_cells) return;
-    const uint32_t off = list_off[cell], n = list_off[cell + 1] - off;
-    if (n < 2 || n > SORT_CAP) return;
-    int x0, y0, cw, ch;
-    cell_rect(G, (int)(cell % G.ncx), (int)(cell / G.ncx), x0, y0, cw, ch);
-    // centre ray of the cell
-    const float u = -1.f + ((float)x0 + 0.5f * (float)(cw - 1)) / G.half_w, v = -1.f + ((float)y0 + 0.5f * (float)(ch - 1)) / G.half_h;
-    float d[3];
-    for (int i = 0; i < 3; ++i) d[i] = (G.inv0[i] * u + G.inv1[i] * v) + G.inv3[i] - G.origin[i];
-    const float inv = rsqrtf(fmaxf(dot3(d, d), 1e-30f));
-    uint32_t m = 2;
-    while (m < n) m <<= 1;
-    float *key = s_key[w];
-    uint32_t *val = s_val[w];
-    for (uint32_t i = lane; i < m; i += 32)
-    {
-        if (i < n)
-        {
-            const uint32_t gi = list_idx[off + i];
-            const float4 a = cullrec[2 * gi];
-            // a non-finite or huge depth (overflowing centre, NaN) is clamped below the padding key, so the padding always
-            // stays behind every real entry and no 0xFFFFFFFF index can reach the first n slots
-            const float k = (a.x * d[0] + a.y * d[1] + a.z * d[2]) * inv;
-            key[i] = (k == k) ? fminf(fmaxf(k, -2.9e38f), 2.9e38f) : 2.9e38f;
-            val[i] = gi;
-        }
-        else
-        {
-            key[i] = __int_as_float(0x7f800000); // +inf
-            val[i] = 0xFFFFFFFFu;
-        }
-    }
-    __syncwarp();
-    for (uint32_t k = 2; k <= m; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1)
-        {
-            for (uint32_t i = lane; i < m; i += 32)
-            {
-                const uint32_t l = i ^ j;
-                if (l > i)
-                {
-                    const float ki = key[i], kl = key[l];
-                    const uint32_t vi = val[i], vl = val[l];
-                    const bool up = (i & k) == 0;
-                    const bool gt = ki > kl || (ki == kl && vi > vl);
-                    if (gt == up)
-                    {
-                        key[i] = kl; key[l] = ki;
-                        val[i] = vl; val[l] = vi;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    for (uint32_t i = lane; i < n; i += 32) list_idx[off + i] = val[i];
-}
 
 // exclusive scan of n counts into n+1 offsets; single CTA of 1024 threads (n <= a few million)
 __global__ void __launch_bounds__(1024) k1_scan(const uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets, uint32_t n)
@@ -395,6 +232,15 @@ __global__ void __launch_bounds__(1024) k1_scan(const uint32_t *__restrict__ cou
         run += counts[i];
     }
     if (threadIdx.x == 1023) offsets[n] = s_part[1023];
+}
+
+// sum of n 32-bit counts in 64 bits (the exclusive scans produce 32-bit offsets: a grand total past 2^32 must be seen, not wrapped)
+__global__ void __launch_bounds__(256) k1_total64(const uint32_t *__restrict__ counts, uint32_t n, unsigned long long *__restrict__ total)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = i < n ? counts[i] : 0u;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
 }
 
 // Large arrays are scanned in three launches: per-tile sums (SCAN_TILE elements per CTA), k1_scan over the tile sums,
@@ -468,6 +314,10 @@ struct TileStats
     unsigned long long n_items;    // work items queued (cells + extra slices of split cells)
     unsigned long long n_split;    // items that belong to split cells (= partial-radiance slots)
     unsigned long long terms_term; // K2b: terms dropped by the transmittance early exit
+    unsigned long long leaf_entries; // k1_leaf: list entries reserved (the bump cursor; may exceed the index array's capacity)
+    unsigned long long bin_entries;  // k1_bin: bin list entries needed
+    int slice;                       // emitters per work item of split cells chosen for this frame (k1_pick_slice)
+    int pad;
 };
 
 __device__ __forceinline__ uint32_t cell_list_id(const FrameGeom &G, int cx, int cy)
@@ -492,23 +342,29 @@ __device__ __forceinline__ void cell_rect(const FrameGeom &G, int cx, int cy, in
     h = min(CELL_H, G.tile_h - ly);
 }
 
+// emitters per work item of split cells: fixed by the host (a pinned slice / after the tile call returned) or, inside the
+// tile call, chosen on the device from the frame's own statistics (k1_pick_slice) so that no host round trip is needed
+__device__ __forceinline__ uint32_t frame_slice(const FrameGeom &G) { return G.slice > 0 ? (uint32_t)G.slice : (uint32_t)*G.slice_dev; }
+
 // number of work items of a cell with an n-entry list
 __device__ __forceinline__ uint32_t cell_items(const FrameGeom &G, uint32_t n, uint32_t cell)
 {
-    const uint32_t slice = (uint32_t)G.slice;
+    const uint32_t slice = frame_slice(G);
     if (n <= 3u * slice || cell >= (1u << ITEM_CELL_BITS)) return 1u;
     const uint32_t k = (n + slice - 1) / slice;
     return k <= (1u << (32 - ITEM_CELL_BITS)) ? k : 1u;
 }
 
 // COUNT_ITEMS = false: listed terms and per-row cost; true: work items per list-length key (needs the frame's slice size)
+constexpr uint32_t HIST_KEYS = 8192; // key = min(n, HIST_KEYS - 1); the queue is filled in descending key order
 template <bool COUNT_ITEMS>
-__global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
+__global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_cnt, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
                         double *__restrict__ row_cost, int cy_begin, int cy_end)
 {
     const int ncells = (cy_end - cy_begin) * G.ncx;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double terms = 0.0;
+    uint32_t items = 0, split = 0;
     if (i < ncells)
     {
         const int cx = i % G.ncx, cy = cy_begin + i / G.ncx;
@@ -516,15 +372,14 @@ __global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_off
         cell_rect(G, cx, cy, x0, y0, w, h);
         const int ya = max(y0, G.row_begin), yb = min(y0 + h, G.row_end);
         const uint32_t id = cell_list_id(G, cx, cy);
-        const uint32_t n = list_off[id + 1] - list_off[id];
+        const uint32_t n = list_cnt[id];
         if (yb > ya)
         {
             if (COUNT_ITEMS)
             {
-                const uint32_t items = cell_items(G, n, (uint32_t)(cy * G.ncx + cx));
-                atomicAdd(&hist[min(n, 65535u)], items);
-                atomicAdd(&stats->n_items, (unsigned long long)items);
-                if (items > 1) atomicAdd(&stats->n_split, (unsigned long long)items);
+                items = cell_items(G, n, (uint32_t)(cy * G.ncx + cx));
+                atomicAdd(&hist[min(n, HIST_KEYS - 1u)], items);
+                split = items > 1 ? items : 0u;
             }
             else
             {
@@ -533,19 +388,29 @@ __global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_off
             }
         }
     }
-    if (!COUNT_ITEMS)
+    // one atomic per warp for the frame totals (a per-thread atomic on one address serialises the whole launch)
+    if (COUNT_ITEMS)
     {
-        // warp reduction of the listed terms
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            items += __shfl_xor_sync(0xffffffffu, items, o);
+            split += __shfl_xor_sync(0xffffffffu, split, o);
+        }
+        if ((threadIdx.x & 31) == 0 && items) atomicAdd(&stats->n_items, (unsigned long long)items);
+        if ((threadIdx.x & 31) == 0 && split) atomicAdd(&stats->n_split, (unsigned long long)split);
+    }
+    else
+    {
         for (int o = 16; o > 0; o >>= 1) terms += __shfl_xor_sync(0xffffffffu, terms, o);
         if ((threadIdx.x & 31) == 0 && terms != 0.0) atomicAdd(&stats->terms_listed, terms);
     }
 }
 
-__global__ void k1_list_stats(const uint32_t *__restrict__ list_off, uint32_t n_lists, TileStats *__restrict__ stats)
+__global__ void k1_list_stats(const uint32_t *__restrict__ list_cnt, uint32_t n_lists, TileStats *__restrict__ stats)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = 0;
-    if (i < n_lists) n = list_off[i + 1] - list_off[i];
+    if (i < n_lists) n = list_cnt[i];
     uint32_t mx = n;
     unsigned long long sum = n;
     for (int o = 16; o > 0; o >>= 1)
@@ -560,14 +425,39 @@ __global__ void k1_list_stats(const uint32_t *__restrict__ list_off, uint32_t n_
     }
 }
 
-// hist (ascending key) -> start position of each key in a DESCENDING ordering; single CTA
-__global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist)
+// Slice size of split cells, chosen on the device (the host-side twin is auto_slice in vrt_cuda.cu): as large as possible
+// (every item repeats pass A), but no item may exceed a quarter of the average work per resident warp, or the longest lists
+// would decide the frame time on small frames.
+__global__ void k1_pick_slice(TileStats *__restrict__ stats, int *__restrict__ slice_dev, int pinned_slice, double warps)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int slice = pinned_slice;
+    if (slice <= 0)
+    {
+        const double per_warp = stats->terms_listed / warps;
+        slice = SLICE_MAX;
+        while (slice > SLICE_MIN && 160.0 * slice * (double)stats->max_list > per_warp / 4.0) slice /= 2;
+    }
+    *slice_dev = slice;
+    stats->slice = slice;
+}
+
+// hist (ascending key) -> start position of each key in a DESCENDING ordering; single CTA.  Also leaves, in stats->n_big, the
+// number of items whose list is longer than the banded kernel's cache (they lead the queue).
+__global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist, TileStats *__restrict__ stats)
 {
     __shared__ uint32_t s_part[1024];
-    // thread t owns keys [t*64, t*64+64) ; descending order => process from the top
+    constexpr int PER = HIST_KEYS / 1024;
+    // thread t owns keys [t*PER, t*PER+PER) counted from the top: descending order
     const int t = threadIdx.x;
+    uint32_t c[PER];
     uint32_t sum = 0;
-    for (int k = 0; k < 64; ++k) sum += hist[65535 - (t * 64 + k)];
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+    {
+        c[k] = hist[HIST_KEYS - 1 - (t * PER + k)];
+        sum += c[k];
+    }
     s_part[t] = sum;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1)
@@ -578,17 +468,18 @@ __global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist
         __syncthreads();
     }
     uint32_t run = s_part[t] - sum;
-    for (int k = 0; k < 64; ++k)
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
     {
-        const int key = 65535 - (t * 64 + k);
-        const uint32_t c = hist[key];
+        const int key = HIST_KEYS - 1 - (t * PER + k);
         hist[key] = run;
-        run += c;
+        if (key == WIN_CAP) stats->n_big = run; // items with a longer list start the queue
+        run += c[k];
     }
 }
 
-__global__ void k1_order(const FrameGeom G, const uint32_t *__restrict__ list_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, uint32_t *__restrict__ cell_slot,
-                         uint32_t *__restrict__ split_cursor, int cy_begin, int cy_end)
+__global__ void k1_order(const FrameGeom G, const uint32_t *__restrict__ list_cnt, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, uint32_t *__restrict__ cell_slot,
+                         uint32_t *__restrict__ split_cursor, int cy_begin, int cy_end, uint32_t queue_cap)
 {
     const int ncells = (cy_end - cy_begin) * G.ncx;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -598,11 +489,12 @@ __global__ void k1_order(const FrameGeom G, const uint32_t *__restrict__ list_of
     cell_rect(G, cx, cy, x0, y0, w, h);
     if (min(y0 + h, G.row_end) <= max(y0, G.row_begin)) return;
     const uint32_t id = cell_list_id(G, cx, cy);
-    const uint32_t n = list_off[id + 1] - list_off[id];
+    const uint32_t n = list_cnt[id];
     const uint32_t cell = (uint32_t)(cy * G.ncx + cx);
     const uint32_t items = cell_items(G, n, cell);
-    const uint32_t pos = atomicAdd(&cursor[min(n, 65535u)], items);
-    for (uint32_t k = 0; k < items; ++k) queue[pos + k] = cell | (k << ITEM_CELL_BITS);
+    const uint32_t pos = atomicAdd(&cursor[min(n, HIST_KEYS - 1u)], items);
+    for (uint32_t k = 0; k < items; ++k)
+        if (pos + k < queue_cap) queue[pos + k] = cell | (k << ITEM_CELL_BITS);
     // split cells get `items` consecutive slots of the partial-radiance buffer (the slot order is irrelevant: K3' sums a
     // cell's slices in slice order)
     cell_slot[cell] = items > 1 ? atomicAdd(split_cursor, items) : NO_SLOT;

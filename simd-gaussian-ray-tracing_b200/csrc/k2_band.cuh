@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
         const PixelRay ray = pixel_ray(G, px, py);
         const uint32_t lid = cell_list_id(G, cx, cy);
         const uint32_t off = args.list_off[lid];
-        const uint32_t n = min(args.list_off[lid + 1] - off, (uint32_t)WIN_CAP); // (longer lists never reach this kernel)
+        const uint32_t n = min(args.list_cnt[lid], (uint32_t)WIN_CAP); // (longer lists never reach this kernel)
         const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
-        const uint32_t q_begin = slot != NO_SLOT ? slice * (uint32_t)G.slice : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + (uint32_t)G.slice) : n;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * frame_slice(G) : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + frame_slice(G)) : n;
 
         // stage the whole list (occluder part) once
         __syncwarp();

@@ -9,7 +9,8 @@ struct RenderArgs
 {
     FrameGeom geom;            // the frame (by value: nothing about a frame lives in per-device state)
     const Rec *rec;            // frame records
-    const uint32_t *list_off;  // per list: [off, off+n)
+    const uint32_t *list_off;  // per list: entries [off, off + cnt) of list_idx (or of rec when the lists are contiguous)
+    const uint32_t *list_cnt;
     const uint32_t *list_idx;  // indices into rec, or nullptr when lists are contiguous ranges of rec
     const uint32_t *queue;     // cost-ordered cell ids
     uint32_t n_queue;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 
         const uint32_t lid = cell_list_id(G, cx, cy);
         const uint32_t off = args.list_off[lid];
-        const uint32_t n = args.list_off[lid + 1] - off;
+        const uint32_t n = args.list_cnt[lid];
 
         auto load_rec = [&](uint32_t k) -> const Rec * {
             const uint32_t gi = args.list_idx ? args.list_idx[off + k] : off + k;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
         // a split cell's item covers the emitters [q_begin, q_end) only; every item still needs all n occluders
         const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
-        const uint32_t q_begin = slot != NO_SLOT ? slice * (uint32_t)G.slice : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + (uint32_t)G.slice) : n;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * frame_slice(G) : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + frame_slice(G)) : n;
         for (uint32_t q0 = q_begin; q0 < q_end; q0 += Q)
         {
             // emitter block
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 }
 
 // K3', split cells: sum the slices' partial radiances in slice order (deterministic) and write the pixel.
-__global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, const uint32_t *__restrict__ list_off, int cy_begin, int cy_end)
+__global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, int cy_begin, int cy_end)
 {
     const FrameGeom &G = args.geom;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, const u
     const uint32_t slot = args.cell_slot[cell];
     if (slot == NO_SLOT) return;
     const uint32_t lid = cell_list_id(G, cx, cy);
-    const uint32_t items = cell_items(G, list_off[lid + 1] - list_off[lid], cell);
+    const uint32_t items = cell_items(G, args.list_cnt[lid], cell);
     float4 L = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t k = 0; k < items; ++k)
     {

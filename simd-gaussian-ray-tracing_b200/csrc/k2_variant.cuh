@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_variant(const RenderArgs arg
         const PixelRay ray = pixel_ray(G, px, py);
         const uint32_t lid = cell_list_id(G, cx, cy);
         const uint32_t off = args.list_off[lid];
-        const uint32_t n = args.list_off[lid + 1] - off;
+        const uint32_t n = args.list_cnt[lid];
         auto load_rec = [&](uint32_t k) -> const Rec * { return args.rec + (args.list_idx ? args.list_idx[off + k] : off + k); };
         // occluder j for this lane: mu_bar, weight A = sigma c sqrt(pi/2) Exp(-d^2 / 2 sigma^2), r = 1/(sqrt2 sigma)
         auto occluder = [&](const Rec *rc, float &mu, float &A, float &r) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_variant(const RenderArgs arg
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
         unsigned long long exec = 0;
         const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
-        const uint32_t q_begin = slot != NO_SLOT ? slice * (uint32_t)G.slice : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + (uint32_t)G.slice) : n;
+        const uint32_t q_begin = slot != NO_SLOT ? slice * frame_slice(G) : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + frame_slice(G)) : n;
         for (uint32_t q0 = q_begin; q0 < q_end; q0 += VQ)
         {
             float s[VQ][5], acc[VQ][5], wgt[VQ];

@@ -49,6 +49,7 @@ struct FrameGeom
     float half_w, half_h; // W/2, H/2 as float
     // float-accumulated tile centres (src/vrt/rt.cpp:47-49): 1024 + 1024 floats in the context's own device buffer
     const float *tile_cx, *tile_cy;
+    const int *slice_dev; // the slice size chosen on the device during the tile call (read when `slice` is 0)
 };
 // The geometry travels by value in every kernel's parameter block (the frame is stateless on the device: two contexts, or
 // two frames of one context, can be in flight on the same GPU -- the re-entrancy of the reference's entries).

@@ -40,6 +40,7 @@ namespace
 {
 #include "vrt_common.cuh"
 #include "k1_tile.cuh"
+#include "k1_bin.cuh"
 #include "k2_render.cuh"
 #include "k2_variant.cuh"
 #include "k2_band.cuh"
@@ -69,8 +70,9 @@ struct vrt_cuda_ctx
     DevBuf aos;        // scene, n x 10 floats
     DevBuf rec;        // frame records
     DevBuf cullrec;    // reference tiling projection
-    DevBuf lvl_counts[4], lvl_offsets[4], lvl_idx[4], lvl_group_off; // coarse culling levels
-    DevBuf ccounts, coffsets, cidx;       // level 1 (cells / tiles)
+    DevBuf bin_count, bin_off, bin_idx;   // per-Gaussian screen binning (k1_bin)
+    DevBuf ccounts, coffsets, cidx;       // the lists K2 walks: entries [coffsets[l], coffsets[l] + ccounts[l]) of cidx
+    DevBuf slice_dev;                     // slice size chosen on the device during the tile call
     DevBuf hist, queue, stats, counter, rowcost, scan_tmp, cell_slot, partial;
     DevBuf tile_centres; // 2 x 1024 floats: the reference's float-accumulated tile centres of the current frame
     DevBuf scene_info;   // K0: max |albedo| bits, non-monotone flag
@@ -89,7 +91,7 @@ struct vrt_cuda_ctx
     DevBuf out_image, out_rad;
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
     DevBuf tile_off;
-    DevBuf lit_offsets, lit_idx; // literal lists (tile_gaussians membership) kept for vrt_cuda_get_lists while K2 uses the visible lists
+    DevBuf lit_offsets, lit_counts, lit_idx; // literal lists (tile_gaussians membership) kept for vrt_cuda_get_lists while K2 uses the visible lists
 
     // state of the last tile()
     bool have_lists = false;
@@ -99,8 +101,9 @@ struct vrt_cuda_ctx
     FrameGeom geom{};
     uint32_t n_lists = 0;
     uint64_t n_entries = 0;
-    uint32_t n_queue = 0;
+    uint32_t n_queue = 0, queue_cap = 0;
     int cy_begin = 0, cy_end = 0;
+    uint64_t bin_hint = 0, idx_hint = 0; // capacities (entries) that sufficed for the previous frame
     uint32_t launches = 0, render_launches = 0; // kernels of the last tile() / render()
     // literal list modes with culling: the lists K2 walks are "literal membership AND visible from the cell" (see
     // visible_pass); what the literal lists were is kept here
@@ -292,9 +295,14 @@ int auto_slice(const vrt_cuda_ctx *ctx, double share)
     return slice;
 }
 
-int build_queue(vrt_cuda_ctx *ctx)
+// Statistics, slice choice, cost histogram and the descending-cost work queue of the band's cells.  Everything is enqueued
+// on the context's stream; nothing is read back here.  queue_cap_hint > 0: the queue is sized from that bound (bounded per-cell
+// lists: cells + entries / SLICE_MIN) and there is no host round trip at all; 0: the item count is read back once (literal
+// list modes, whose per-cell item counts have no useful a-priori bound).  The caller reads the TileStats after its own final
+// synchronisation (finish_tile).
+int build_queue(vrt_cuda_ctx *ctx, uint64_t queue_cap_hint)
 {
-    const FrameGeom &G = ctx->geom;
+    FrameGeom &G = ctx->geom;
     // cell rows intersecting the band
     int cyb = G.ncy, cye = 0;
     for (int cy = 0; cy < G.ncy; ++cy)
@@ -309,44 +317,56 @@ int build_queue(vrt_cuda_ctx *ctx)
     }
     ctx->cy_begin = cyb;
     ctx->cy_end = cye;
-    const int ncells = (cye - cyb) * G.ncx;
-    if (int rc = reserve(ctx, ctx->hist, sizeof(uint32_t) * 65536)) return rc;
-    if (int rc = reserve(ctx, ctx->stats, sizeof(TileStats))) return rc;
+    const int ncells = std::max(0, cye - cyb) * G.ncx;
+    if (int rc = reserve(ctx, ctx->hist, sizeof(uint32_t) * HIST_KEYS)) return rc;
     if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
     if (int rc = reserve(ctx, ctx->rowcost, sizeof(double) * (size_t)G.ncy)) return rc;
-    CU(cudaMemsetAsync(ctx->hist.p, 0, sizeof(uint32_t) * 65536, ctx->stream));
-    CU(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TileStats), ctx->stream));
+    if (int rc = reserve(ctx, ctx->slice_dev, sizeof(int))) return rc;
+    if (int rc = reserve(ctx, ctx->cell_slot, sizeof(uint32_t) * (size_t)G.ncx * G.ncy)) return rc;
+    CU(cudaMemsetAsync(ctx->hist.p, 0, sizeof(uint32_t) * HIST_KEYS, ctx->stream));
     CU(cudaMemsetAsync(ctx->rowcost.p, 0, sizeof(double) * (size_t)G.ncy, ctx->stream));
-    const uint32_t *loff = (const uint32_t *)ctx->coffsets.p;
-    const int tb = 256, gb = (ncells + tb - 1) / tb;
-    k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(loff, ctx->n_lists, (TileStats *)ctx->stats.p);
-    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(G, loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, (double *)ctx->rowcost.p, cyb, cye);
-    TileStats ts;
-    CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemsetAsync((uint32_t *)ctx->counter.p + 2, 0, sizeof(uint32_t), ctx->stream));
+    // the slice size is chosen on the device (k1_pick_slice) and read through G.slice_dev until the tile call has returned
+    G.slice = 0;
+    G.slice_dev = (const int *)ctx->slice_dev.p;
+    TileStats *stats = (TileStats *)ctx->stats.p;
+    const uint32_t *lcnt = (const uint32_t *)ctx->ccounts.p;
+    const int tb = 256, gb = std::max(1, (ncells + tb - 1) / tb);
+    k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(lcnt, ctx->n_lists, stats);
+    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, stats, (double *)ctx->rowcost.p, cyb, cye);
+    k1_pick_slice<<<1, 32, 0, ctx->stream>>>(stats, (int *)ctx->slice_dev.p, ctx->tune_slice, (double)ctx->sm_count * 12.0);
+    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, stats, nullptr, cyb, cye);
+    k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p, stats);
+    uint64_t cap = queue_cap_hint;
+    if (cap == 0)
     {
-        // Slice size of split cells: as large as possible (every item repeats pass A), but no item may exceed a quarter of
-        // the average work per resident warp, or the longest lists would decide the frame time on small frames.
-        ctx->q_terms_listed = ts.terms_listed;
-        ctx->q_max_list = (uint32_t)ts.max_list;
-        ctx->geom.slice = ctx->tune_slice ? ctx->tune_slice : auto_slice(ctx, 1.0);
+        TileStats ts;
+        CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cap = ts.n_items;
     }
-    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(G, loff, (uint32_t *)ctx->hist.p, (TileStats *)ctx->stats.p, nullptr, cyb, cye);
-    k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p);
-    // descending order: the start slot of key WIN_CAP = number of items with a longer list (they lead the queue)
-    CU(cudaMemcpyAsync(&((TileStats *)ctx->stats.p)->n_big, (const uint32_t *)ctx->hist.p + WIN_CAP, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    // the queue holds one item per cell plus the extra slices of split cells: size it from the counts k1_hist produced
+    if (cap > 0xFFFFFFF0ull) return fail(ctx, VRT_CUDA_E_NOMEM, "work queue of %llu items", (unsigned long long)cap);
+    if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max<uint64_t>(cap, 1))) return rc;
+    ctx->queue_cap = (uint32_t)cap;
+    k1_order<<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye,
+                                       (uint32_t)cap);
+    ctx->launches += 6;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// End of a tile call: the one host synchronisation.  Reads the frame's statistics (queue length, split cells, slice, the
+// entry counts the capacity checks need) and fixes the slice size in the host copy of the geometry.
+int finish_tile(vrt_cuda_ctx *ctx, TileStats &ts)
+{
     CU(cudaMemcpyAsync(&ts, ctx->stats.p, sizeof(ts), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->n_queue = (uint32_t)ts.n_items;
+    ctx->q_terms_listed = ts.terms_listed;
+    ctx->q_max_list = (uint32_t)ts.max_list;
+    ctx->n_queue = (uint32_t)std::min<unsigned long long>(ts.n_items, ctx->queue_cap);
     ctx->n_split = (uint32_t)ts.n_split;
     ctx->n_big = (uint32_t)ts.n_big;
-    if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max<uint32_t>(ctx->n_queue, 1))) return rc;
-    if (int rc = reserve(ctx, ctx->cell_slot, sizeof(uint32_t) * (size_t)G.ncx * G.ncy)) return rc;
-    CU(cudaMemsetAsync((uint32_t *)ctx->counter.p + 2, 0, sizeof(uint32_t), ctx->stream));
-    k1_order<<<gb, tb, 0, ctx->stream>>>(G, loff, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye);
-    ctx->launches += 5;
-    CU(cudaGetLastError());
+    ctx->geom.slice = ts.slice > 0 ? ts.slice : SLICE_MAX;
     return 0;
 }
 
@@ -544,14 +564,11 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     if (ctx->abort_stream) { cudaStreamSynchronize(ctx->abort_stream); cudaStreamDestroy(ctx->abort_stream); }
     if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
     if (ctx->abort_dev) cudaFree(ctx->abort_dev);
-    DevBuf *bufs[] = {&ctx->tile_centres, &ctx->scene_info, &ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx,
-                      &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off, &ctx->lit_offsets, &ctx->lit_idx};
+    DevBuf *bufs[] = {&ctx->tile_centres, &ctx->scene_info, &ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx, &ctx->bin_count, &ctx->bin_off,
+                      &ctx->bin_idx, &ctx->slice_dev, &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial,
+                      &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off, &ctx->lit_offsets, &ctx->lit_counts, &ctx->lit_idx};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
-    for (int i = 0; i < 4; ++i)
-        for (DevBuf *b : {&ctx->lvl_counts[i], &ctx->lvl_offsets[i], &ctx->lvl_idx[i]})
-            if (b->p) cudaFree(b->p);
-    if (ctx->lvl_group_off.p) cudaFree(ctx->lvl_group_off.p);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -830,7 +847,112 @@ int vrt_cuda_mix_peak(vrt_cuda_ctx *ctx, int nf, int nm, int nl, double *steps_p
     return 0;
 }
 
-// K0 + K1 for one frame: records, lists of the frame's list mode, depth sort, work queue
+// host-side constants of the binning grid (k1_bin.cuh): the two families of planes through the apex, one per screen axis
+static BinGrid make_bin_grid(const FrameGeom &G)
+{
+    BinGrid B{};
+    B.nbx = (G.ncx + BIN_CX - 1) / BIN_CX;
+    B.nby = (G.ncy + BIN_CY - 1) / BIN_CY;
+    float Wv[3];
+    for (int i = 0; i < 3; ++i) Wv[i] = G.inv3[i] - G.origin[i];
+    auto cross = [](const float *a, const float *b, float *r) {
+        r[0] = a[1] * b[2] - a[2] * b[1];
+        r[1] = a[2] * b[0] - a[0] * b[2];
+        r[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto dot = [](const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    cross(G.inv1, G.inv0, B.px); // x planes contain U = inv1 and the ray u R + Wv: n(u) = U x (u R + Wv)
+    cross(G.inv1, Wv, B.qx);
+    cross(G.inv0, G.inv1, B.py); // y planes contain R = inv0: n(v) = R x (v U + Wv)
+    cross(G.inv0, Wv, B.qy);
+    B.pp_x = dot(B.px, B.px); B.pq_x = dot(B.px, B.qx); B.qq_x = dot(B.qx, B.qx);
+    B.pp_y = dot(B.py, B.py); B.pq_y = dot(B.py, B.qy); B.qq_y = dot(B.qy, B.qy);
+    B.u_min = -1.f; B.u_max = -1.f + (float)(G.W - 1) / G.half_w;
+    B.v_min = -1.f; B.v_max = -1.f + (float)(G.H - 1) / G.half_h;
+    return B;
+}
+
+// K1 for per-cell lists: binning + the fused cull / sort pass.  src_tiles = true: the candidates of a cell are the records of
+// its reference tile (caller-supplied tiles_t), not a bin list.  Capacities come from the previous frame (or a first guess) and
+// are checked by the caller after the frame's one synchronisation.
+static int enqueue_cell_lists(vrt_cuda_ctx *ctx, const FrameGeom &G, uint64_t n_records, bool src_tiles, const uint32_t *tile_off)
+{
+    const uint64_t cells = (uint64_t)G.ncx * G.ncy;
+    if (cells > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "image too large");
+    TileStats *stats = (TileStats *)ctx->stats.p;
+    LeafArgs L{};
+    L.cullrec = (const float4 *)ctx->cullrec.p;
+    if (!src_tiles)
+    {
+        const BinGrid B = make_bin_grid(G);
+        const uint64_t nb = (uint64_t)B.nbx * B.nby;
+        if (int rc = reserve(ctx, ctx->bin_count, sizeof(uint32_t) * nb)) return rc;
+        if (int rc = reserve(ctx, ctx->bin_off, sizeof(uint32_t) * (nb + 1))) return rc;
+        const uint64_t want = std::max<uint64_t>(ctx->bin_hint, std::max<uint64_t>(4 * n_records, 1u << 20));
+        if (int rc = reserve(ctx, ctx->bin_idx, sizeof(uint32_t) * want)) return rc;
+        const uint64_t bin_cap = std::min<uint64_t>(ctx->bin_idx.cap / sizeof(uint32_t), 0xFFFFFFF0ull);
+        const unsigned grid = (unsigned)((n_records + 255) / 256);
+        CU(cudaMemsetAsync(ctx->bin_count.p, 0, sizeof(uint32_t) * nb, ctx->stream));
+        if (n_records) k1_bin<false><<<grid, 256, 0, ctx->stream>>>(G, B, (const float4 *)ctx->cullrec.p, (uint32_t)n_records, (uint32_t *)ctx->bin_count.p, nullptr, nullptr, 0, &stats->bin_entries);
+        ctx->launches++;
+        if (int rc = scan_u32(ctx, (const uint32_t *)ctx->bin_count.p, (uint32_t *)ctx->bin_off.p, (uint32_t)nb)) return rc;
+        CU(cudaMemsetAsync(ctx->bin_count.p, 0, sizeof(uint32_t) * nb, ctx->stream));
+        if (n_records) k1_bin<true><<<grid, 256, 0, ctx->stream>>>(G, B, (const float4 *)ctx->cullrec.p, (uint32_t)n_records, (uint32_t *)ctx->bin_count.p, (const uint32_t *)ctx->bin_off.p,
+                                                   (uint32_t *)ctx->bin_idx.p, bin_cap, nullptr);
+        ctx->launches++;
+        L.bin_off = (const uint32_t *)ctx->bin_off.p;
+        L.bin_count = (const uint32_t *)ctx->bin_count.p;
+        L.bin_idx = (const uint32_t *)ctx->bin_idx.p;
+        L.bin_cap = bin_cap;
+        L.nbx = B.nbx;
+    }
+    else L.tile_off = tile_off;
+    if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * cells)) return rc;
+    if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (cells + 1))) return rc;
+    // first guess for the index array: 96 entries per cell of the band (BASELINE configs 4/5 need ~70-85)
+    const uint64_t band_cells = (uint64_t)G.ncx * ((uint64_t)(G.row_end - G.row_begin + CELL_H - 1) / CELL_H + 1);
+    const uint64_t want = std::max<uint64_t>(ctx->idx_hint, band_cells * 96 + (1u << 16));
+    if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * want)) return rc;
+    L.list_off = (uint32_t *)ctx->coffsets.p;
+    L.list_cnt = (uint32_t *)ctx->ccounts.p;
+    L.list_idx = (uint32_t *)ctx->cidx.p;
+    L.cursor = &stats->leaf_entries;
+    L.idx_cap = std::min<uint64_t>(ctx->cidx.cap / sizeof(uint32_t), 0xFFFFFFF0ull);
+    L.n_cells = (uint32_t)cells;
+    const unsigned grid = (unsigned)((cells + LEAF_WARPS - 1) / LEAF_WARPS);
+    if (src_tiles) k1_leaf<1><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
+    else k1_leaf<0><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
+    ctx->launches++;
+    ctx->n_lists = (uint32_t)cells;
+    ctx->lists_sorted = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// after the frame's synchronisation: did the bin lists and the index array fit?  (false: capacities were raised, run again)
+static int cell_lists_fit(vrt_cuda_ctx *ctx, const TileStats &ts, bool &fit)
+{
+    fit = true;
+    if (ts.leaf_entries > 0xFFFFFFF0ull || ts.bin_entries > 0xFFFFFFF0ull)
+        return fail(ctx, VRT_CUDA_E_NOMEM, "more than 2^32 list entries in this frame (%llu cell entries, %llu bin entries): render it in row bands or tighten bound_sigmas",
+                    (unsigned long long)ts.leaf_entries, (unsigned long long)ts.bin_entries);
+    if (ts.bin_entries > ctx->bin_idx.cap / sizeof(uint32_t))
+    {
+        ctx->bin_hint = ts.bin_entries + ts.bin_entries / 4 + 4096;
+        fit = false;
+    }
+    else ctx->bin_hint = std::max<uint64_t>(ctx->bin_hint / 2, ts.bin_entries + ts.bin_entries / 8 + 4096);
+    if (ts.leaf_entries > ctx->cidx.cap / sizeof(uint32_t))
+    {
+        ctx->idx_hint = ts.leaf_entries + ts.leaf_entries / 4 + 4096;
+        fit = false;
+    }
+    else ctx->idx_hint = std::max<uint64_t>(ctx->idx_hint / 2, ts.leaf_entries + ts.leaf_entries / 8 + 4096);
+    ctx->n_entries = ts.leaf_entries;
+    return 0;
+}
+
+// K0 + K1 for one frame: records, lists of the frame's list mode (depth-sorted for the per-cell modes), work queue
 static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
@@ -850,6 +972,7 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
     if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(N, 1))) return rc;
     if (int rc = reserve(ctx, ctx->cullrec, 2 * sizeof(float4) * std::max<uint64_t>(N, 1))) return rc;
     if (int rc = reserve(ctx, ctx->scene_info, sizeof(uint32_t) * 4)) return rc;
+    if (int rc = reserve(ctx, ctx->stats, sizeof(TileStats))) return rc;
     CU(cudaMemsetAsync(ctx->scene_info.p, 0, sizeof(uint32_t) * 4, ctx->stream));
     if (N)
     {
@@ -857,121 +980,73 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
                                                                          (uint32_t *)ctx->scene_info.p);
         ctx->launches++;
     }
-
-    if (G.list_kind == 2)
-    {
-        // single list: all Gaussians, contiguous
-        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * 2)) return rc;
-        const uint32_t off[2] = {0u, (uint32_t)N};
-        CU(cudaMemcpyAsync(ctx->coffsets.p, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream)); // off[] is on the stack
-        ctx->n_lists = 1;
-        ctx->n_entries = N;
-    }
-    else if (G.list_kind == 1)
-    {
-        const uint32_t nt = (uint32_t)(G.tiles_x * G.tiles_y);
-        if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * nt)) return rc;
-        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (nt + 1))) return rc;
-        k1_cull_tiles<false><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, (uint32_t *)ctx->ccounts.p, nullptr, nullptr, nt);
-        k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, nt);
-        uint32_t total = 0;
-        CU(cudaMemcpyAsync(&total, (const uint32_t *)ctx->coffsets.p + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
-        k1_cull_tiles<true><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nullptr, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, nt);
-        ctx->launches += 3;
-        ctx->n_lists = nt;
-        ctx->n_entries = total;
-    }
-    else
-    {
-        // levels from coarse to fine: groups of 64x128, 16x32, 4x8 and 1x1 cells (512, 128, 32 pixels square, then the
-        // 8x4-pixel cell); a level is dropped when it would not be coarser than the whole grid
-        std::vector<CullLevel> levels;
-        const int gxs[4] = {64, 16, 4, 1}, gys[4] = {128, 32, 8, 1};
-        for (int i = 0; i < 4; ++i)
-        {
-            if (i < 3 && gxs[i] >= G.ncx && gys[i] >= G.ncy && !levels.empty()) continue;
-            if (i < 3 && gxs[i + 1] >= G.ncx && gys[i + 1] >= G.ncy) continue; // the next finer level is still one group
-            CullLevel L{};
-            L.gx = gxs[i]; L.gy = gys[i];
-            L.ngx = (G.ncx + L.gx - 1) / L.gx; L.ngy = (G.ncy + L.gy - 1) / L.gy;
-            L.is_root = levels.empty() ? 1 : 0;
-            if (L.is_root) L.n_seg = (int)std::max<uint64_t>(1, (N + ROOT_SEG - 1) / ROOT_SEG);
-            else
-            {
-                // enough warps to fill the GPU: groups that intersect the row band x segments >= 16 warps per SM
-                const int px_h = L.gy * CELL_H; // group height in pixels (uniform grids; an estimate otherwise)
-                const int rows_hit = std::max(1, std::min(L.ngy, (G.row_end + px_h - 1) / px_h) - std::min(L.ngy - 1, G.row_begin / px_h));
-                const int64_t active = (int64_t)L.ngx * rows_hit;
-                L.n_seg = (int)std::min<int64_t>(32, std::max<int64_t>(1, ((int64_t)ctx->sm_count * 16 + active - 1) / active));
-            }
-            if (!levels.empty()) { L.pgx = levels.back().gx; L.pgy = levels.back().gy; L.pngx = levels.back().ngx; }
-            levels.push_back(L);
-        }
-        const uint32_t *parent_off = nullptr, *parent_idx = nullptr;
-        for (size_t li = 0; li < levels.size(); ++li)
-        {
-            const CullLevel &L = levels[li];
-            const bool last = li + 1 == levels.size();
-            const uint64_t groups = (uint64_t)L.ngx * L.ngy, work = groups * L.n_seg;
-            if (work > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "scene x image too large for culling level %zu", li);
-            DevBuf &cnt = last ? ctx->ccounts : ctx->lvl_counts[li];
-            DevBuf &off = last ? ctx->coffsets : ctx->lvl_offsets[li];
-            DevBuf &idx = last ? ctx->cidx : ctx->lvl_idx[li];
-            if (int rc = reserve(ctx, cnt, sizeof(uint32_t) * work)) return rc;
-            if (int rc = reserve(ctx, off, sizeof(uint32_t) * (work + 1))) return rc;
-            const unsigned grid = (unsigned)((work * 32 + 255) / 256);
-            k1_cull<false><<<grid, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx,
-                                                         (uint32_t *)cnt.p, nullptr, nullptr, (uint32_t)work);
-            if (int rc = scan_u32(ctx, (const uint32_t *)cnt.p, (uint32_t *)off.p, (uint32_t)work)) return rc;
-            uint32_t total = 0;
-            CU(cudaMemcpyAsync(&total, (const uint32_t *)off.p + work, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            if (int rc = reserve(ctx, idx, sizeof(uint32_t) * std::max<uint32_t>(total, 1))) return rc;
-            k1_cull<true><<<grid, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, L, parent_off, parent_idx, nullptr,
-                                                        (const uint32_t *)off.p, (uint32_t *)idx.p, (uint32_t)work);
-            ctx->launches += 2;
-            parent_idx = (const uint32_t *)idx.p;
-            if (L.n_seg > 1)
-            {
-                // per-(group, segment) offsets -> per-group offsets for the next level
-                if (int rc = reserve(ctx, ctx->lvl_group_off, sizeof(uint32_t) * (groups + 1))) return rc;
-                k1_group_offsets<<<(unsigned)((groups + 256) / 256), 256, 0, ctx->stream>>>((const uint32_t *)off.p, (uint32_t *)ctx->lvl_group_off.p, (uint32_t)groups, L.n_seg);
-                ctx->launches++;
-                parent_off = (const uint32_t *)ctx->lvl_group_off.p;
-                if (last)
-                {
-                    // a single-level hierarchy with a segmented root: the cell offsets are the group offsets
-                    CU(cudaMemcpyAsync(ctx->coffsets.p, ctx->lvl_group_off.p, sizeof(uint32_t) * (groups + 1), cudaMemcpyDeviceToDevice, ctx->stream));
-                }
-            }
-            else parent_off = (const uint32_t *)off.p;
-            if (last)
-            {
-                ctx->n_lists = (uint32_t)groups;
-                ctx->n_entries = total;
-            }
-        }
-    }
     ctx->tiled_list_mode = frame->flags & VRT_CUDA_LIST_MASK;
     ctx->tiled_tiles_x = G.tiles_x;
     ctx->tiled_tiles_y = G.tiles_y;
     ctx->tiled_bound = G.bound_k;
     ctx->lists_sorted = false;
-    // bounded per-cell lists are always depth-sorted: the order is deterministic (ties by index) and makes most occluders
-    // sign-uniform for an emitter block (K2), and saturated in depth-window mode
-    if (G.list_kind == 0 && ctx->n_entries)
+    TileStats ts{};
+
+    if (G.list_kind == 0)
     {
-        k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>(ctx->geom, (const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
-        ctx->launches++;
-        ctx->lists_sorted = true;
+        // bounded per-cell lists: no host round trip inside; capacities from the previous frame, checked afterwards
+        for (int attempt = 0;; ++attempt)
+        {
+            CU(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TileStats), ctx->stream));
+            if (int rc = enqueue_cell_lists(ctx, G, N, false, nullptr)) return rc;
+            const uint64_t queue_cap = (uint64_t)G.ncx * G.ncy + ctx->cidx.cap / sizeof(uint32_t) / SLICE_MIN + 1;
+            if (int rc = build_queue(ctx, std::min<uint64_t>(queue_cap, 0xFFFFFFF0ull))) return rc;
+            CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            if (int rc = finish_tile(ctx, ts)) return rc;
+            bool fit = true;
+            if (int rc = cell_lists_fit(ctx, ts, fit)) return rc;
+            if (fit) break;
+            if (attempt >= 2) return fail(ctx, VRT_CUDA_E_NOMEM, "list capacities did not converge");
+        }
     }
-    CU(cudaGetLastError());
-    if (int rc = build_queue(ctx)) return rc;
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    else
+    {
+        CU(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TileStats), ctx->stream));
+        if (G.list_kind == 2)
+        {
+            // single list: all Gaussians, contiguous
+            if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * 2)) return rc;
+            if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * 2)) return rc;
+            const uint32_t off[2] = {0u, (uint32_t)N}, cnt[2] = {(uint32_t)N, 0u};
+            CU(cudaMemcpyAsync(ctx->coffsets.p, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->ccounts.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream)); // off[] / cnt[] are on the stack
+            ctx->n_lists = 1;
+            ctx->n_entries = N;
+        }
+        else
+        {
+            // the literal membership of tile_gaussians, one list per reference tile, ascending Gaussian index (count, scan, write)
+            const uint32_t nt = (uint32_t)(G.tiles_x * G.tiles_y);
+            if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * nt)) return rc;
+            if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (nt + 1))) return rc;
+            if (int rc = reserve(ctx, ctx->scan_tmp, sizeof(unsigned long long))) return rc;
+            k1_cull_tiles<false><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, (uint32_t *)ctx->ccounts.p, nullptr, nullptr, nt);
+            // the grand total in 64 bits: 32-bit offsets wrap silently past 2^32 entries (tiles x N can get there)
+            CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->leaf_entries, 0, sizeof(unsigned long long), ctx->stream));
+            k1_total64<<<(nt + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, nt, &((TileStats *)ctx->stats.p)->leaf_entries);
+            k1_scan<<<1, 1024, 0, ctx->stream>>>((const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, nt);
+            unsigned long long total = 0;
+            CU(cudaMemcpyAsync(&total, &((TileStats *)ctx->stats.p)->leaf_entries, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (total > 0xFFFFFFF0ull)
+                return fail(ctx, VRT_CUDA_E_NOMEM, "the literal tile lists hold %llu entries (more than 2^32): use a *_BOUND list mode or fewer tiles", total);
+            if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint64_t>(total, 1))) return rc;
+            k1_cull_tiles<true><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nullptr, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, nt);
+            ctx->launches += 4;
+            ctx->n_lists = nt;
+            ctx->n_entries = total;
+        }
+        CU(cudaGetLastError());
+        if (int rc = build_queue(ctx, 0)) return rc;
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (int rc = finish_tile(ctx, ts)) return rc;
+    }
     CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
     ctx->have_lists = true;
     return 0;
@@ -988,6 +1063,7 @@ static int keep_literal(vrt_cuda_ctx *ctx)
     CU(cudaMemcpyAsync(&ctx->lit_stats, ctx->stats.p, sizeof(TileStats), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     std::swap(ctx->coffsets, ctx->lit_offsets);
+    std::swap(ctx->ccounts, ctx->lit_counts);
     std::swap(ctx->cidx, ctx->lit_idx);
     ctx->lit_kind = ctx->geom.list_kind;
     ctx->lit_n_lists = ctx->n_lists;
@@ -1027,11 +1103,12 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
     const uint64_t total = offsets[n_tiles];
     if (total > 0x7FFFFFF0ull) return fail(ctx, VRT_CUDA_E_INVALID, "tile lists too long (device indices are 32-bit)");
     if (total && !aos_concat) return fail(ctx, VRT_CUDA_E_INVALID, "aos_concat is NULL");
-    std::vector<uint32_t> off32(n_tiles + 1);
+    std::vector<uint32_t> off32(n_tiles + 1), cnt32(n_tiles + 1, 0u);
     for (uint64_t t = 0; t <= n_tiles; ++t)
     {
         if (t && offsets[t] < offsets[t - 1]) return fail(ctx, VRT_CUDA_E_INVALID, "offsets must be non-decreasing");
         off32[t] = (uint32_t)offsets[t];
+        if (t) cnt32[t - 1] = (uint32_t)(offsets[t] - offsets[t - 1]);
     }
     ctx->have_lists = false;
     ctx->literal = false;
@@ -1045,8 +1122,10 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
     if (int rc = reserve(ctx, ctx->rec, sizeof(Rec) * std::max<uint64_t>(total, 1))) return rc;
     if (int rc = reserve(ctx, ctx->cullrec, 2 * sizeof(float4) * std::max<uint64_t>(total, 1))) return rc;
     if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (n_tiles + 1))) return rc;
+    if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * (n_tiles + 1))) return rc;
     if (total) CU(cudaMemcpyAsync(ctx->tile_aos.p, aos_concat, total * 40, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->coffsets.p, off32.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->ccounts.p, cnt32.data(), sizeof(uint32_t) * (n_tiles + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (total)
     {
         k0_prepare<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(G, (const float *)ctx->tile_aos.p, total, (Rec *)ctx->rec.p, (float4 *)ctx->cullrec.p,
@@ -1058,11 +1137,13 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
     ctx->n_entries = total;
     ctx->lists_from_host = true;
     ctx->lists_sorted = false;
-    if (int rc = build_queue(ctx)) return rc;
+    if (int rc = reserve(ctx, ctx->stats, sizeof(TileStats))) return rc;
+    CU(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TileStats), ctx->stream));
+    TileStats ts{};
+    if (int rc = build_queue(ctx, 0)) return rc; // (synchronises: off32 / cnt32 have been consumed)
     if (total && !(frame->flags & VRT_CUDA_NO_SKIP))
     {
-        // visible lists (see vrt_cuda_tile): one cull level, every 8x4 cell scans the record range of its own tile
-        CU(cudaStreamSynchronize(ctx->stream)); // off32 (stack) is consumed before the offsets buffer changes hands
+        // visible lists (see vrt_cuda_tile): every 8x4 cell scans the record range of its own tile once (k1_leaf)
         if (int rc = keep_literal(ctx)) return rc;
         FrameGeom V = G;
         V.list_kind = 0;
@@ -1070,40 +1151,26 @@ int vrt_cuda_set_tile_lists(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, cons
         V.use_bound = 1;
         V.bound_k = VISIBLE_SIGMAS;
         ctx->geom = V; // (same tile-centre buffer)
-        CullLevel L{};
-        L.gx = L.gy = 1;
-        L.ngx = V.ncx; L.ngy = V.ncy;
-        L.pgx = V.cptx; L.pgy = V.cpty; L.pngx = V.tiles_x;
-        L.is_root = 0; L.n_seg = 1;
-        const uint64_t cells = (uint64_t)V.ncx * V.ncy;
-        if (cells > 0x7FFFFFFFull / 32) return fail(ctx, VRT_CUDA_E_INVALID, "image too large");
-        if (int rc = reserve(ctx, ctx->ccounts, sizeof(uint32_t) * cells)) return rc;
-        if (int rc = reserve(ctx, ctx->coffsets, sizeof(uint32_t) * (cells + 1))) return rc;
-        const unsigned grid = (unsigned)((cells * 32 + 255) / 256);
-        k1_cull<false><<<grid, 256, 0, ctx->stream>>>(V, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr,
-                                                     (uint32_t *)ctx->ccounts.p, nullptr, nullptr, (uint32_t)cells);
-        if (int rc = scan_u32(ctx, (const uint32_t *)ctx->ccounts.p, (uint32_t *)ctx->coffsets.p, (uint32_t)cells)) return rc;
-        uint32_t kept = 0;
-        CU(cudaMemcpyAsync(&kept, (const uint32_t *)ctx->coffsets.p + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint32_t>(kept, 1))) return rc;
-        k1_cull<true><<<grid, 256, 0, ctx->stream>>>(V, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)total, L, (const uint32_t *)ctx->lit_offsets.p, nullptr, nullptr,
-                                                    (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, (uint32_t)cells);
-        ctx->launches += 2;
-        ctx->n_lists = (uint32_t)cells;
-        ctx->n_entries = kept;
-        if (kept)
+        for (int attempt = 0;; ++attempt)
         {
-            k1_sort_cells<<<(ctx->n_lists + 3) / 4, 128, 0, ctx->stream>>>(ctx->geom, (const float4 *)ctx->cullrec.p, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, ctx->n_lists);
-            ctx->launches++;
-            ctx->lists_sorted = true;
+            CU(cudaMemsetAsync(ctx->stats.p, 0, sizeof(TileStats), ctx->stream));
+            if (int rc = enqueue_cell_lists(ctx, V, total, true, (const uint32_t *)ctx->lit_offsets.p)) return rc;
+            const uint64_t queue_cap = (uint64_t)V.ncx * V.ncy + ctx->cidx.cap / sizeof(uint32_t) / SLICE_MIN + 1;
+            if (int rc = build_queue(ctx, std::min<uint64_t>(queue_cap, 0xFFFFFFF0ull))) return rc;
+            CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            if (int rc = finish_tile(ctx, ts)) return rc;
+            bool fit = true;
+            if (int rc = cell_lists_fit(ctx, ts, fit)) return rc;
+            if (fit) break;
+            if (attempt >= 2) return fail(ctx, VRT_CUDA_E_NOMEM, "list capacities did not converge");
         }
-        CU(cudaGetLastError());
-        if (int rc = build_queue(ctx)) return rc;
         ctx->literal = true;
     }
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream)); // off32 lives on this stack frame
+    else
+    {
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (int rc = finish_tile(ctx, ts)) return rc;
+    }
     CU(cudaEventElapsedTime(&ctx->ms_tile, ctx->ev[0], ctx->ev[1]));
     ctx->have_lists = true;
     return 0;
@@ -1119,28 +1186,42 @@ int vrt_cuda_get_lists(vrt_cuda_ctx *ctx, uint32_t *counts_out, uint64_t counts_
     const uint64_t n_entries = ctx->literal ? ctx->lit_n_entries : ctx->n_entries;
     const int kind = ctx->literal ? ctx->lit_kind : ctx->geom.list_kind;
     const DevBuf &offsets = ctx->literal ? ctx->lit_offsets : ctx->coffsets;
+    const DevBuf &counts = ctx->literal ? ctx->lit_counts : ctx->ccounts;
     const DevBuf &indices = ctx->literal ? ctx->lit_idx : ctx->cidx;
     if (n_cells_out) *n_cells_out = n_lists;
     if (n_entries_out) *n_entries_out = n_entries;
+    std::vector<uint32_t> cnt(n_lists);
+    if ((counts_out || idx_out) && n_lists)
+    {
+        CU(cudaMemcpyAsync(cnt.data(), counts.p, sizeof(uint32_t) * n_lists, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     if (counts_out)
     {
         if (counts_cap < n_lists) return fail(ctx, VRT_CUDA_E_INVALID, "counts_cap too small");
-        std::vector<uint32_t> off(n_lists + 1);
-        CU(cudaMemcpyAsync(off.data(), offsets.p, sizeof(uint32_t) * off.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t i = 0; i < n_lists; ++i) counts_out[i] = off[i + 1] - off[i];
+        for (uint32_t i = 0; i < n_lists; ++i) counts_out[i] = cnt[i];
     }
     if (idx_out)
     {
         if (idx_cap < n_entries) return fail(ctx, VRT_CUDA_E_INVALID, "idx_cap too small");
-        if (kind == 2 || ctx->lists_from_host)
+        if (kind == 2 || (ctx->lists_from_host && kind == 1))
         {
             for (uint64_t i = 0; i < n_entries; ++i) idx_out[i] = (uint32_t)i;
         }
         else if (n_entries)
         {
-            CU(cudaMemcpyAsync(idx_out, indices.p, sizeof(uint32_t) * n_entries, cudaMemcpyDeviceToHost, ctx->stream));
+            // lists are (offset, count) pairs placed anywhere in the index array: return them concatenated in list order
+            std::vector<uint32_t> off(n_lists), all(n_entries);
+            CU(cudaMemcpyAsync(off.data(), offsets.p, sizeof(uint32_t) * n_lists, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(all.data(), indices.p, sizeof(uint32_t) * n_entries, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
+            uint64_t at = 0;
+            for (uint32_t i = 0; i < n_lists; ++i)
+            {
+                if ((uint64_t)off[i] + cnt[i] > n_entries || at + cnt[i] > n_entries) return fail(ctx, VRT_CUDA_E_STATE, "inconsistent list table");
+                std::memcpy(idx_out + at, all.data() + off[i], sizeof(uint32_t) * cnt[i]);
+                at += cnt[i];
+            }
         }
     }
     return 0;
@@ -1222,6 +1303,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.geom = G;
     a.rec = (const Rec *)ctx->rec.p;
     a.list_off = (const uint32_t *)ctx->coffsets.p;
+    a.list_cnt = (const uint32_t *)ctx->ccounts.p;
     a.list_idx = (G.list_kind == 2 || (ctx->lists_from_host && !ctx->literal)) ? nullptr : (const uint32_t *)ctx->cidx.p;
     if (ctx->literal && (frame->flags & VRT_CUDA_NO_SKIP))
         return fail(ctx, VRT_CUDA_E_STATE, "these lists were built with culling: pass VRT_CUDA_NO_SKIP to vrt_cuda_tile / vrt_cuda_set_tile_lists as well");
@@ -1267,7 +1349,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     if (ctx->n_split)
     {
         const uint32_t ncells = (uint32_t)((ctx->cy_end - ctx->cy_begin) * G.ncx);
-        k3_combine<<<(unsigned)(((uint64_t)ncells * 32 + 255) / 256), 256, 0, ctx->stream>>>(a, (const uint32_t *)ctx->coffsets.p, ctx->cy_begin, ctx->cy_end);
+        k3_combine<<<(unsigned)(((uint64_t)ncells * 32 + 255) / 256), 256, 0, ctx->stream>>>(a, ctx->cy_begin, ctx->cy_end);
         ctx->render_launches++;
     }
     CU(cudaGetLastError());

@@ -145,7 +145,7 @@ def test_kernels_under_address_sanitizer(build_emu):
     lib = build_emu.build(asan=True)
     small = "tests/test_gpu_small_frames.py::"
     selection = [small + "test_split_cells_and_bands_small", small + "test_contiguous_lists_through_the_bulk_copy_staging",
-                 small + "test_k1_hierarchy_full_depth_and_bands", "tests/test_gpu_parity.py::test_empty_scene_and_ragged_image", "tests/test_gpu_parity.py::test_row_bands_compose",
+                 small + "test_k1_bins_cells_and_bands", "tests/test_gpu_parity.py::test_empty_scene_and_ragged_image", "tests/test_gpu_parity.py::test_row_bands_compose",
                  "tests/test_gpu_parity.py::test_scene_out_of_view_renders_black_in_every_list_mode"]
     if os.environ.get("VRT_EMU_FULL") == "1":
         selection += [small + "test_depth_window_small", small + "test_depth_window_long_lists_take_the_in_loop_test", small + "test_register_block_and_packing_variants_small",

@@ -199,9 +199,9 @@ def test_randomised_small_frames(pkg, renderer):
     print(f"worst max-abs radiance error over 120 random frames: {worst:.3e}")
 
 
-def test_k1_hierarchy_full_depth_and_bands(pkg, renderer):
-    """Tile-only: an image large enough for all four cull levels (1024 x 768: 128 x 192 cells), reference tiles that are not
-    square, a row band that cuts through groups of every level.  The band's lists must be exactly the full frame's lists for
+def test_k1_bins_cells_and_bands(pkg, renderer):
+    """Tile-only: 1024 x 768 (32 x 24 bins of 32 x 32 pixels, 128 x 192 cells), reference tiles that are not square, a row band
+    that cuts through bins.  The band's lists must be exactly the full frame's lists for
     the cells it renders and empty elsewhere; sampled cells are conservative against the exact per-ray criterion and no
     longer than the four-plane box (as tests/test_gpu_parity.py checks at 256^2 with a single level pair)."""
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
@@ -245,4 +245,12 @@ def test_k1_hierarchy_full_depth_and_bands(pkg, renderer):
             box = set(np.nonzero(cpu_lists.rect_bound_member(scene, origin, planes, k * 1.001))[0].tolist())
             assert need <= got <= box, (cell, sorted(need - got), sorted(got - box))
             n_got, n_box = n_got + len(got), n_box + len(box)
+            # the list is in depth order along the cell's centre ray (what the banded kernel walks), ties by Gaussian index
+            order = idx[offs[cell] : offs[cell + 1]].astype(np.int64)
+            centre = np.array([[cx * 8 + 3.5, cyy * 4 + 1.5]])
+            inv = np.linalg.inv(np.asarray(cam.view_matrix, np.float64).reshape(4, 4).T)
+            u, v = -1.0 + centre[0, 0] / (W / 2.0), -1.0 + centre[0, 1] / (H / 2.0)
+            d = inv[:3, 0] * u + inv[:3, 1] * v + inv[:3, 3] - np.asarray(origin, np.float64)[:3]
+            depth = (scene[order, 4:7].astype(np.float64) - np.asarray(origin, np.float64)[:3]) @ (d / np.linalg.norm(d))
+            assert np.all(np.diff(depth) >= -1e-5), (cell, depth)
         assert n_got <= n_box
