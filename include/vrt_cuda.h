@@ -237,6 +237,8 @@ int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, u
 /* Kernel tuning knob for benchmarks (not part of the reference's surface): emitters per register block
  * Q in {2,4,6,8} and packed f32x2 arithmetic on (1) / off (0).  Defaults are the tuned values. */
 int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
+/* Resident CTAs per SM of the banded kernel: 4 (default, 128 registers) or 5 (96 registers); a benchmarking knob. */
+int vrt_cuda_set_band_tuning(vrt_cuda_ctx *ctx, int ctas_per_sm);
 
 /* Work items of heavy cells.  A cell whose list is longer than 3 x slice entries is rendered as ceil(n / slice) independent
  * items (emitter ranges) whose partial radiances are summed in slice order; the fp32 result depends on the grouping, so two

@@ -309,7 +309,7 @@ extern "C"
     }
 
     /// The app's frame (main.cpp:257-297) for one mode: tile_gaussians + the mode's render entry.
-    /// mode 1/4/5/8 as in main.cpp:150-177.  times_ms_out = {tiling, draw}.  Returns list-term count
+    /// mode 1..8 as in main.cpp:150-177.  times_ms_out = {tiling, draw}.  Returns list-term count
     /// sum_t P_t*5*n_t^2 (tiled modes) or W*H*5*N^2 (untiled) through terms_out.
     int ref_render_app(int mode, const float *aos, uint64_t n, uint64_t w, uint64_t h, uint64_t tiles_per_axis,
                        uint64_t threads, float camera_offset, float focal, float initial_rot,
@@ -326,9 +326,15 @@ extern "C"
         f64 t1 = now_ms();
         switch (mode)
         {
+        // the eight instantiations of main.cpp:269-294 (modes 2/6: the default Radiance = radiance<simd_transmittance>,
+        // SIMD over occluders, rt.h:61-95; modes 3/7: simd_radiance, SIMD over emitters, rt.h:166-199)
         case 1: res = render_image<radiance<transmittance>>(w, h, image, c.cam, c.origin, gaussians, running); break;
+        case 2: res = render_image(w, h, image, c.cam, c.origin, gaussians, running); break;
+        case 3: res = render_image<simd_radiance>(w, h, image, c.cam, c.origin, gaussians, running); break;
         case 4: res = simd_render_image(w, h, image, c.cam, c.origin, gaussians, running); break;
         case 5: res = render_image<radiance<transmittance>>(w, h, image, c.cam, c.origin, tiles, running, threads); break;
+        case 6: res = render_image(w, h, image, c.cam, c.origin, tiles, running, threads); break;
+        case 7: res = render_image<simd_radiance>(w, h, image, c.cam, c.origin, tiles, running, threads); break;
         case 8: res = simd_render_image(w, h, image, c.cam, c.origin, tiles, running, threads); break;
         default: simd::aligned_free(image); delete gaussians.soa_gaussians; return -1;
         }

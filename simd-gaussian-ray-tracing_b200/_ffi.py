@@ -75,6 +75,7 @@ CUDA_SYMBOLS = {
     "vrt_cuda_unpin_buffer": (c_i, [vp, vp]),
     "vrt_cuda_row_costs": (c_i, [vp, vp, c_u32, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32)]),
     "vrt_cuda_set_tuning": (c_i, [vp, c_i, c_i]),
+    "vrt_cuda_set_band_tuning": (c_i, [vp, c_i]),
     "vrt_cuda_fp32_peak": (c_i, [vp, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_term_peak": (c_i, [vp, c_i, c_i, ctypes.POINTER(c_d)]),
     "vrt_cuda_mix_peak": (c_i, [vp, c_i, c_i, c_i, ctypes.POINTER(c_d)]),

@@ -126,38 +126,45 @@ __global__ void __launch_bounds__(256) k1_bin(const FrameGeom G, const BinGrid B
     }
 }
 
-// ---- per-warp sorts of (key, value) pairs, ascending by key, ties by value ------------------------------------------------
-__device__ __forceinline__ bool pair_less(float ka, uint32_t va, float kb, uint32_t vb) { return ka < kb || (ka == kb && va < vb); }
-
-// n <= 128: rank of every element by counting (n^2 / 32 comparisons per lane, no barriers inside); writes out[rank] = value
-__device__ __forceinline__ void warp_rank_sort(const float *key, const uint32_t *val, uint32_t n, uint32_t *out, int lane)
+// ---- per-warp sorts ----------------------------------------------------------------------------------------------------
+// An entry is one 64-bit word: (order-preserving bits of the depth key) << 32 | Gaussian index, so "ascending by depth, ties
+// by index" is a single unsigned comparison and the sorted order is a pure function of the frame.
+__device__ __forceinline__ unsigned long long sort_word(float key, uint32_t val)
 {
-    float k[4];
-    uint32_t v[4], rank[4];
+    const uint32_t b = __float_as_uint(key);
+    const uint32_t o = b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u); // unsigned order = float order (keys are never NaN)
+    return ((unsigned long long)o << 32) | val;
+}
+
+// n <= 32 M: rank of every element by counting (n^2 / 32 comparisons per lane, no barriers inside); writes out[rank] = index
+template <int M>
+__device__ __forceinline__ void warp_rank_sort(const unsigned long long *kv, uint32_t n, uint32_t *out, int lane)
+{
+    unsigned long long mine[M];
+    uint32_t rank[M];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < M; ++m)
     {
         const uint32_t i = (uint32_t)lane + 32u * m;
-        k[m] = i < n ? key[i] : 0.f;
-        v[m] = i < n ? val[i] : 0u;
+        mine[m] = i < n ? kv[i] : 0xFFFFFFFFFFFFFFFFull;
         rank[m] = 0;
     }
+#pragma unroll 4
     for (uint32_t j = 0; j < n; ++j)
     {
-        const float kj = key[j];
-        const uint32_t vj = val[j];
+        const unsigned long long other = kv[j];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) rank[m] += pair_less(kj, vj, k[m], v[m]) ? 1u : 0u;
+        for (int m = 0; m < M; ++m) rank[m] += other < mine[m] ? 1u : 0u;
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
-        if ((uint32_t)lane + 32u * m < n) out[rank[m]] = v[m];
+    for (int m = 0; m < M; ++m)
+        if ((uint32_t)lane + 32u * m < n) out[rank[m]] = (uint32_t)mine[m];
 }
 
 // Bitonic sorting network in its all-ascending form (every merge starts with a "flip" step, partner i ^ (k - 1), then the
-// half-cleaners i ^ j): every compare-exchange leaves the smaller pair at the lower index, so the n real entries behave as if
+// half-cleaners i ^ j): every compare-exchange leaves the smaller word at the lower index, so the n real entries behave as if
 // padded with +inf up to the next power of two without the padding ever being stored -- a partner at or beyond n is a no-op.
-__device__ __forceinline__ void warp_bitonic_sort(float *key, uint32_t *val, uint32_t n, int lane)
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long *kv, uint32_t n, int lane)
 {
     uint32_t m = 2;
     while (m < n) m <<= 1;
@@ -170,12 +177,11 @@ __device__ __forceinline__ void warp_bitonic_sort(float *key, uint32_t *val, uin
                 const uint32_t l = (j == k) ? (i ^ (k - 1)) : (i ^ (j >> 1));
                 if (l > i && l < n)
                 {
-                    const float ki = key[i], kl = key[l];
-                    const uint32_t vi = val[i], vl = val[l];
-                    if (pair_less(kl, vl, ki, vi))
+                    const unsigned long long a = kv[i], b = kv[l];
+                    if (b < a)
                     {
-                        key[i] = kl; key[l] = ki;
-                        val[i] = vl; val[l] = vi;
+                        kv[i] = b;
+                        kv[l] = a;
                     }
                 }
             }
@@ -204,8 +210,7 @@ __device__ void warp_bitonic_sort_global(uint32_t *idx, uint32_t n, const float4
                 if (l > i && l < n)
                 {
                     const uint32_t vi = idx[i], vl = idx[l];
-                    const float ki = depth_key(cullrec[2 * vi], d), kl = depth_key(cullrec[2 * vl], d);
-                    if (pair_less(kl, vl, ki, vi))
+                    if (sort_word(depth_key(cullrec[2 * vl], d), vl) < sort_word(depth_key(cullrec[2 * vi], d), vi))
                     {
                         idx[i] = vl;
                         idx[l] = vi;
@@ -233,8 +238,7 @@ struct LeafArgs
 template <int SRC>
 __global__ void __launch_bounds__(LEAF_WARPS * 32) k1_leaf(const FrameGeom G, const LeafArgs L)
 {
-    __shared__ float s_key[LEAF_WARPS][LEAF_CAP];
-    __shared__ uint32_t s_val[LEAF_WARPS][LEAF_CAP];
+    __shared__ unsigned long long s_kv[LEAF_WARPS][LEAF_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t cell = blockIdx.x * LEAF_WARPS + w;
     if (cell >= L.n_cells) return;
@@ -265,17 +269,19 @@ __global__ void __launch_bounds__(LEAF_WARPS * 32) k1_leaf(const FrameGeom G, co
         for (int i = 0; i < 3; ++i) d[i] = (G.inv0[i] * u + G.inv1[i] * v) + G.inv3[i] - G.origin[i];
         const float inv = rsqrtf(fmaxf(dot3(d, d), 1e-30f));
         for (int i = 0; i < 3; ++i) d[i] *= inv;
-        float *key = s_key[w];
-        uint32_t *val = s_val[w];
+        unsigned long long *kv = s_kv[w];
+        // the index of the NEXT step's candidate is fetched one step ahead (index -> record is a dependent pair of loads)
+        uint32_t gi_next = (SRC == 0 && begin + lane < end) ? L.bin_idx[begin + lane] : begin + lane;
         for (uint32_t k = begin; k < end; k += 32)
         {
             const uint32_t e = k + lane;
             bool pass = false;
-            uint32_t gi = 0;
+            const uint32_t gi = gi_next;
+            if (SRC == 0) { if (e + 32 < end) gi_next = L.bin_idx[e + 32]; }
+            else gi_next = e + 32;
             float kd = 0.f;
             if (e < end)
             {
-                gi = SRC == 0 ? L.bin_idx[e] : e;
                 const float4 a = L.cullrec[2 * gi]; // (oc.xyz, sigma)
                 const float4 cr = G.use_ref ? L.cullrec[2 * gi + 1] : make_float4(0.f, 0.f, 0.f, 1.f);
                 pass = cull_test(G, rc, a, a.w, cr);
@@ -283,11 +289,7 @@ __global__ void __launch_bounds__(LEAF_WARPS * 32) k1_leaf(const FrameGeom G, co
             }
             const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
             const uint32_t pos = n + __popc(ballot & ((1u << lane) - 1u));
-            if (pass && pos < (uint32_t)LEAF_CAP)
-            {
-                key[pos] = kd;
-                val[pos] = gi;
-            }
+            if (pass && pos < (uint32_t)LEAF_CAP) kv[pos] = sort_word(kd, gi);
             n += __popc(ballot);
         }
         if (n)
@@ -299,11 +301,14 @@ __global__ void __launch_bounds__(LEAF_WARPS * 32) k1_leaf(const FrameGeom G, co
             off = (uint32_t)at;
             __syncwarp();
             if (!fits) { /* counted, not stored */ }
-            else if (n <= 128u) warp_rank_sort(key, val, n, L.list_idx + off, lane);
+            else if (n <= 32u) warp_rank_sort<1>(kv, n, L.list_idx + off, lane);
+            else if (n <= 64u) warp_rank_sort<2>(kv, n, L.list_idx + off, lane);
+            else if (n <= 96u) warp_rank_sort<3>(kv, n, L.list_idx + off, lane);
+            else if (n <= 128u) warp_rank_sort<4>(kv, n, L.list_idx + off, lane);
             else if (n <= (uint32_t)LEAF_CAP)
             {
-                warp_bitonic_sort(key, val, n, lane);
-                for (uint32_t i = lane; i < n; i += 32) L.list_idx[off + i] = val[i];
+                warp_bitonic_sort(kv, n, lane);
+                for (uint32_t i = lane; i < n; i += 32) L.list_idx[off + i] = (uint32_t)kv[i];
             }
             else
             {

@@ -32,7 +32,8 @@ constexpr float TERMINATE_EPS = 1e-6f; // bound on the per-channel radiance drop
 struct BandSmem
 {
     float4 a[WIN_CAP], b[WIN_CAP]; // occluder part of the records
-    float4 fb[WIN_CAP];            // (front_j, back_j, mumax_j, mumin_j); front = -3e38 marks an occluder no lane sees
+    float4 fb[WIN_CAP];            // (front_j, back_j, mumax_j + margin, mumin_j - margin); front = -3e38: no lane sees it
+    float smin1[WIN_CAP];          // mumin_j - 4 sigma_j: shallowest sample depth of emitter j over the warp
     float fmx[WIN_CAP];            // running max of front  : j < f  <=>  fmx[j] <= Smin
     float bmn[WIN_CAP];            // suffix  min of back   : j >= bk <=>  bmn[j] >= Smax
     float srem[WIN_CAP];           // suffix  min of mumin - 4 sigma: shallowest sample of the emitters j, j+1, ...
@@ -47,8 +48,8 @@ __device__ __forceinline__ float ordered_float(int k) { return __int_as_float(k 
 __device__ __forceinline__ float warp_max_f(float x) { return ordered_float(__reduce_max_sync(0xffffffffu, ordered_int(x))); }
 __device__ __forceinline__ float warp_min_f(float x) { return ordered_float(__reduce_min_sync(0xffffffffu, ordered_int(x))); }
 
-template <int ERF>
-__global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs args, uint32_t queue_begin)
+template <int ERF, int MINB>
+__global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArgs args, uint32_t queue_begin)
 {
     __shared__ BandSmem s_band[BAND_WARPS];
     constexpr int Q = BAND_Q;
@@ -121,8 +122,11 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
                 fm = fmaxf(fm, front);
                 if (lane == 0)
                 {
-                    sm.fb[j] = make_float4(front, alive ? mumin - half : 3.0e38f, mumax, mumin);
+                    // the sign tests of pass B carry a depth margin: a sample within a few ulp of the centre takes the signed body
+                    const float margin = 2e-6f * fmaxf(fabsf(mumax), fabsf(mumin));
+                    sm.fb[j] = make_float4(front, alive ? mumin - half : 3.0e38f, mumax + margin, mumin - margin);
                     sm.fmx[j] = fm;
+                    sm.smin1[j] = mumin - 4.f * b.w;
                 }
             }
             __syncwarp();
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
                 {
                     const float4 fbj = sm.fb[j];
                     vb = fbj.y;
-                    vs = fbj.w - 4.f * sm.b[j].w;
+                    vs = sm.smin1[j];
                     vs = (vs == vs) ? vs : -3.0e38f; // a NaN depth never licenses an exit
                 }
 #pragma unroll
@@ -175,10 +179,25 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
         // ---- pass B ----
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
         unsigned long long exec = 0, sat = 0, term = 0;
-        uint32_t f = 0, bk = 0; // window [f, bk); Pf = sum_{j<f} A_j, Pb = sum_{j<bk} A_j (per lane)
-        uint32_t nf = 0, nb = 0; // visible entries among [0, f) and [0, bk)
+        // window [f, bk) of the current block; Pf = sum_{j<f} A_j, Pb = sum_{j<bk} A_j (per lane); nf / nb count the entries
+        // some lane sees among [0, f) / [0, bk).  The window moves with the blocks WITHOUT extra per-lane work in the common case:
+        // an occluder that enters at the back is evaluated by the block it enters in (its weight is added to Pb there), and one
+        // that leaves at the front was in the previous block's window, where the next block's shallowest sample depth was
+        // already known (its weight was added to Pf there).  The explicit loops below only run at an item's first block, when
+        // the window has to move backwards, or when consecutive windows do not overlap.
+        uint32_t f = 0, bk = 0, nf = 0, nb = 0;
         float Pf = 0.f, Pb = 0.f;
         uint32_t exit_check_at = q_begin; // first block after which the exit test may run again (back-off after a failed test)
+        // uniform sample-depth range of the emitter pair (je, je + 1 if real): [min(mumin - 4 sigma), max(mumax)]
+        auto group_range = [&](uint32_t je, bool two, float &lo, float &hi) {
+            lo = sm.smin1[je];
+            hi = sm.fb[je].z;
+            if (two)
+            {
+                lo = fminf(lo, sm.smin1[je + 1]);
+                hi = fmaxf(hi, sm.fb[je + 1].z);
+            }
+        };
         for (uint32_t q0 = q_begin; q0 < q_end; q0 += Q)
         {
             const uint32_t n_real = min((uint32_t)Q, q_end - q0);
@@ -188,7 +207,6 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
             float s0 = sm.fb[q0].w;
             s0 = (fabsf(s0) <= 3.0e38f) ? s0 : 0.f;
             bool any_emit = false;
-            float smin_g[2], smax_g[2];
 #pragma unroll
             for (int e = 0; e < Q; ++e)
             {
@@ -208,45 +226,58 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
                     s[e][k] = (mu - s0) + (float)(k - 4) * b.w;
                     acc[e][k] = 0.f;
                 }
-                // uniform depth range of the pair group's samples, from the warp-wide centre depths of pass A
-                const float4 fbe = sm.fb[je];
-                const float lo = fbe.w - 4.f * b.w, hi = fbe.z;
-                if ((e & 1) == 0)
-                {
-                    smin_g[e >> 1] = lo;
-                    smax_g[e >> 1] = hi;
-                }
-                else if (real)
-                {
-                    smin_g[e >> 1] = fminf(smin_g[e >> 1], lo);
-                    smax_g[e >> 1] = fmaxf(smax_g[e >> 1], hi);
-                }
             }
             if (!__any_sync(0xffffffffu, any_emit)) continue; // no lane sees any of these emitters
             const bool g1 = n_real > 2;
             const uint32_t ng0 = min(2u, n_real), ng1 = n_real - ng0;
-            const float Smin = g1 ? fminf(smin_g[0], smin_g[1]) : smin_g[0], Smax = g1 ? fmaxf(smax_g[0], smax_g[1]) : smax_g[0];
+            float smin_g[2], smax_g[2];
+            group_range(q0, n_real > 1, smin_g[0], smax_g[0]);
+            smin_g[1] = smin_g[0];
+            smax_g[1] = smax_g[0];
+            if (g1) group_range(q0 + 2, n_real > 3, smin_g[1], smax_g[1]);
+            const float Smin = fminf(smin_g[0], smin_g[1]), Smax = fmaxf(smax_g[0], smax_g[1]);
+            // the next block's shallowest sample depth: what leaves the window after this block
+            float Smin_next = 3.0e38f;
+            if (q0 + Q < q_end)
+            {
+                float lo, hi;
+                group_range(q0 + Q, q0 + Q + 1 < q_end, Smin_next, hi);
+                if (q0 + Q + 2 < q_end)
+                {
+                    group_range(q0 + Q + 2, q0 + Q + 3 < q_end, lo, hi);
+                    Smin_next = fminf(Smin_next, lo);
+                }
+            }
 
-            // move the window: the head [0, f) is in front of every sample of the block, the tail [bk, n) behind
+            // ---- place the window (explicit steps: rare, see above) ----
             while (f < n && sm.fmx[f] <= Smin) { Pf += weight_of(f, nf, 1u); ++f; }
             while (f > 0 && !(sm.fmx[f - 1] <= Smin)) { --f; Pf -= weight_of(f, nf, 0xFFFFFFFFu); }
-            while (bk < n && !(sm.bmn[bk] >= Smax)) { Pb += weight_of(bk, nb, 1u); ++bk; }
             while (bk > 0 && sm.bmn[bk - 1] >= Smax) { --bk; Pb -= weight_of(bk, nb, 0xFFFFFFFFu); }
-            const float base_common = esat * (Pf - (total - Pb));
-            float base0 = base_common, base1 = base_common;
-            sat += (unsigned long long)(nf + (n_alive - max(nb, nf))) * n_real; // head and tail, entries some lane sees
+            while (bk < f) { Pb += weight_of(bk, nb, 1u); ++bk; } // (an empty window in front of f)
+            uint32_t bk_new = bk; // the tail [bk_new, n) is behind every sample of the block: a uniform scan, no per-lane work
+            while (bk_new < n && !(sm.bmn[bk_new] >= Smax)) ++bk_new;
 
-            for (uint32_t j = f; j < bk; ++j)
+            const float Pf_now = Pf;
+            const uint32_t f_now = f, nf_now = nf;
+            float base0 = 0.f, base1 = 0.f;
+            bool leaving = true; // j == f so far: the leading run of the NEXT block can still grow
+            for (uint32_t j = f_now; j < bk_new; ++j)
             {
                 const float4 fbj = sm.fb[j];
-                if (!(fbj.x > -1.0e38f)) continue; // no lane sees it
+                const bool seen = fbj.x > -1.0e38f;
+                leaving = leaving && sm.fmx[j] <= Smin_next;
+                if (!seen) // no lane sees it: weight 0 everywhere
+                {
+                    if (leaving) f = j + 1;
+                    continue;
+                }
                 const float4 a = sm.a[j], b = sm.b[j];
                 float mu, e;
                 occluder_setup(a, b, ray, mu, e);
                 const float A = b.z * e, r = b.x, nm = -(mu - s0) * r;
+                if (j >= bk) { Pb += A; ++nb; }                 // enters the window at the back
+                if (leaving) { Pf += A; ++nf; f = j + 1; }       // in front of every sample of the next block
                 const float2 rr = make_float2(r, r), mm = make_float2(nm, nm);
-                // sign tests carry a depth margin: a sample within a few ulp of the occluder's centre takes the signed body
-                const float margin = 2e-6f * fmaxf(fabsf(fbj.z), fabsf(fbj.w));
 #pragma unroll
                 for (int g = 0; g < 2; ++g)
                 {
@@ -257,8 +288,8 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
                     if (fbj.x <= sming) { base = fmaf(A, esat, base); sat += ng; continue; }  // in front of every sample: erf = +esat
                     if (fbj.y >= smaxg) { base = fmaf(-A, esat, base); sat += ng; continue; } // behind every sample: -esat
                     exec += ng;
-                    const bool pos = fbj.z + margin <= sming; // every sample behind the centre for every lane: t >= 0
-                    const bool neg = fbj.w - margin >= smaxg; // every sample in front of it: t <= 0
+                    const bool pos = fbj.z <= sming; // every sample behind the centre for every lane: t >= 0
+                    const bool neg = fbj.w >= smaxg; // every sample in front of it: t <= 0
                     if (pos || neg)
                     {
                         // erf(t) = +-(1 - w(t)), sign known per (occluder, group): +-A once, -+A w(t) per term
@@ -288,6 +319,12 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
                     }
                 }
             }
+            bk = bk_new;
+            // head [0, f_now) in front of every sample, tail [bk, n) behind: resolved by the two prefix sums
+            const float base_common = esat * (Pf_now - (total - Pb));
+            base0 += base_common;
+            base1 += base_common;
+            sat += (unsigned long long)(nf_now + (n_alive - nb)) * n_real;
             // T(s) = 2^(C - base - acc); pdf at the samples = c_bar e^{-k^2/2}, k = -4..0 (src/vrt/rt.h:153-161)
             float lt_max = -3.0e38f; // log2 T at the block's least occluded sample (k = -4 of every emitter)
 #pragma unroll
@@ -335,7 +372,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k2_band(const RenderArgs a
             }
         }
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
-        else if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
         if (lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
         if (lane == 0 && term) atomicAdd(args.terms_term, term * 5ull * n_live);

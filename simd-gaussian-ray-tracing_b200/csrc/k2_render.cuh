@@ -25,6 +25,7 @@ struct RenderArgs
     uint32_t terminate;              // early exit enabled
     float skip_thresh;         // skip an occluder / emitter for the whole warp when exp2 weight <= thresh (-1: never)
     uint32_t quant_nearest, alpha_from_w;
+    uint32_t image_vec16;      // the image base and row pitch are 16-byte aligned: quads of pixels are stored as one uint4
     uint32_t window; // banded evaluation of depth-sorted lists (k2_band; k2_render<WIN> for lists beyond its cache)
     const uint32_t *cell_slot; // per cell: first slot of its slices in `partial`, NO_SLOT for whole cells (may be null)
     float4 *partial;           // [slot][lane] partial radiance of the items of split cells
@@ -85,26 +86,46 @@ __device__ __forceinline__ void occluder_setup(const float4 a, const float4 b, c
     e = ex2_approx(-d2 * b.y);
 }
 
-// K3: clamp, quantise (truncate | round-to-nearest-even) and pack one pixel; store the packed word and/or the float4 radiance
-__device__ __forceinline__ void store_pixel(const RenderArgs &args, size_t pi, float Lr, float Lg, float Lb, float La)
+// K3: clamp, quantise (truncate | round-to-nearest-even) and pack one pixel (rt.h:238-243 / 329-333, alpha quirk rt.h:373-377)
+__device__ __forceinline__ uint32_t pack_pixel(const RenderArgs &args, float Lr, float Lg, float Lb, float La)
 {
-    if (args.radiance) args.radiance[pi] = make_float4(Lr, Lg, Lb, La);
-    if (args.image)
+    const float r255 = fminf(Lr, 1.f) * 255.f, g255 = fminf(Lg, 1.f) * 255.f, b255 = fminf(Lb, 1.f) * 255.f;
+    uint32_t R, Gc, B, A = 0xFFu;
+    if (args.quant_nearest)
     {
-        const float r255 = fminf(Lr, 1.f) * 255.f, g255 = fminf(Lg, 1.f) * 255.f, b255 = fminf(Lb, 1.f) * 255.f;
-        uint32_t R, Gc, B, A = 0xFFu;
-        if (args.quant_nearest)
-        {
-            R = (uint32_t)__float2int_rn(r255); Gc = (uint32_t)__float2int_rn(g255); B = (uint32_t)__float2int_rn(b255);
-            if (args.alpha_from_w) A = (uint32_t)__float2int_rn(fminf(La, 1.f) * 255.f);
-        }
-        else
-        {
-            R = (uint32_t)r255; Gc = (uint32_t)g255; B = (uint32_t)b255;
-            if (args.alpha_from_w) A = (uint32_t)(fminf(La, 1.f) * 255.f);
-        }
-        args.image[pi] = (A << 24) | (R << 16) | (Gc << 8) | B;
+        R = (uint32_t)__float2int_rn(r255); Gc = (uint32_t)__float2int_rn(g255); B = (uint32_t)__float2int_rn(b255);
+        if (args.alpha_from_w) A = (uint32_t)__float2int_rn(fminf(La, 1.f) * 255.f);
     }
+    else
+    {
+        R = (uint32_t)r255; Gc = (uint32_t)g255; B = (uint32_t)b255;
+        if (args.alpha_from_w) A = (uint32_t)(fminf(La, 1.f) * 255.f);
+    }
+    return (A << 24) | (R << 16) | (Gc << 8) | B;
+}
+
+// Framebuffer write of one 8x4-pixel cell by its warp (lane = pixel, lane = ly * 8 + lx); EVERY lane calls it.
+// The packed words of a row are transposed through three shuffles so that two lanes per row store 16 bytes each: eight
+// 128-bit stores per cell instead of 32 scalar ones (replaces the per-pixel stores and the tile -> image copy of
+// rt.h:373-377, 388-399).  Rows that are not entirely inside the image / band, or a frame whose rows are not 16-byte
+// aligned, fall back to one word per lane.  The optional float4 radiance is one 16-byte store per lane already.
+__device__ __forceinline__ void store_cell(const RenderArgs &args, const FrameGeom &G, int px, int py, bool live, float Lr, float Lg, float Lb, float La)
+{
+    const size_t pi = (size_t)py * G.W + px;
+    if (args.radiance && live) args.radiance[pi] = make_float4(Lr, Lg, Lb, La);
+    if (!args.image) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t w0 = pack_pixel(args, Lr, Lg, Lb, La);
+    const uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2), w3 = __shfl_down_sync(0xffffffffu, w0, 3);
+    // the four lanes of a quad are live together, their pixels are consecutive and the first one is 16-byte aligned
+    const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+    const bool quad = ((live_mask >> (lane & ~3)) & 0xFu) == 0xFu && (pi & 3) == 0 && args.image_vec16;
+    const bool quad_any = __shfl_sync(0xffffffffu, (int)quad, lane & ~3) != 0;
+    if (quad_any)
+    {
+        if ((lane & 3) == 0) *reinterpret_cast<uint4 *>(args.image + pi) = make_uint4(w0, w1, w2, w3);
+    }
+    else if (live) args.image[pi] = w0;
 }
 
 // ray through pixel (px, py): plane = inverse(view) (u, v, 0, 1) (src/vrt/camera.cpp:60-70); dir = normalize(plane - origin)
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 
         // ---- K3: framebuffer ----
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
-        else if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
         if (WIN && lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
         exec = 0;
@@ -399,5 +420,5 @@ __global__ void __launch_bounds__(256) k3_combine(const RenderArgs args, int cy_
     }
     const int lx = lane & (CELL_W - 1), ly = lane >> 3;
     const int px = x0 + lx, py = y0 + ly;
-    if (lx < cw && ly < ch && py >= G.row_begin && py < G.row_end) store_pixel(args, (size_t)py * G.W + px, L.x, L.y, L.z, L.w);
+    store_cell(args, G, px, py, lx < cw && ly < ch && py >= G.row_begin && py < G.row_end, L.x, L.y, L.z, L.w);
 }

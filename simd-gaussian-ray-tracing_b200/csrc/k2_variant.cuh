@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k2_variant(const RenderArgs arg
             }
         }
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La);
-        else if (live) store_pixel(args, (size_t)py * G.W + px, Lr, Lg, Lb, La);
+        else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
     }
 }

@@ -119,6 +119,7 @@ struct vrt_cuda_ctx
     int tune_slice = 0; // 0 = automatic (auto_slice)
     int tune_q = 0; // 0 = automatic: 8 emitters per register block, 4 when the lists are short
     int tune_pack = 1;
+    int tune_band_ctas = 4; // resident CTAs per SM of the banded kernel (4 or 5)
     std::vector<float> centres_host;
     uint32_t tiled_list_mode = 0; // what the current lists were built for (vrt_cuda_render_device checks the frame against it)
     int tiled_tiles_x = 0, tiled_tiles_y = 0;
@@ -416,12 +417,15 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
         }
         if (a.n_queue > n_big)
         {
+            // 4 CTAs of 4 warps per SM (128 registers); 5 (96 registers, a few spills) is kept for comparison (vrt_cuda_set_band_tuning)
             int per_sm = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band<ERF>, BAND_WARPS * 32, 0);
+            if (ctx->tune_band_ctas == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band<ERF, 5>, BAND_WARPS * 32, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band<ERF, 4>, BAND_WARPS * 32, 0);
             if (per_sm < 1) per_sm = 1;
             const uint32_t want = (a.n_queue - n_big + BAND_WARPS - 1) / BAND_WARPS;
             const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
-            k2_band<ERF><<<grid, BAND_WARPS * 32, 0, ctx->stream>>>(a, n_big);
+            if (ctx->tune_band_ctas == 5) k2_band<ERF, 5><<<grid, BAND_WARPS * 32, 0, ctx->stream>>>(a, n_big);
+            else k2_band<ERF, 4><<<grid, BAND_WARPS * 32, 0, ctx->stream>>>(a, n_big);
         }
         return 0;
     }
@@ -722,6 +726,14 @@ int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int q, int pack)
     if (q != 0 && q != 4 && q != 8) return fail(ctx, VRT_CUDA_E_INVALID, "Q must be 0 (auto), 4 or 8");
     ctx->tune_q = q;
     ctx->tune_pack = pack;
+    return 0;
+}
+
+int vrt_cuda_set_band_tuning(vrt_cuda_ctx *ctx, int ctas_per_sm)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (ctas_per_sm != 4 && ctas_per_sm != 5) return fail(ctx, VRT_CUDA_E_INVALID, "the banded kernel runs 4 or 5 CTAs per SM");
+    ctx->tune_band_ctas = ctas_per_sm;
     return 0;
 }
 
@@ -1330,6 +1342,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.partial = (float4 *)ctx->partial.p;
     const bool bounded = G.use_bound != 0;
     a.skip_thresh = (frame->flags & VRT_CUDA_NO_SKIP) ? -1.f : ((bounded && !ctx->literal) ? std::exp2(-0.5f * G.bound_k * G.bound_k * LOG2E) : 0.f);
+    a.image_vec16 = (image_dev && ((uintptr_t)image_dev & 15u) == 0 && (G.W & 3) == 0) ? 1u : 0u;
     a.quant_nearest = (frame->flags & VRT_CUDA_QUANT_NEAREST) ? 1u : 0u;
     a.alpha_from_w = (frame->flags & VRT_CUDA_ALPHA_FROM_W) ? 1u : 0u;
     CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));

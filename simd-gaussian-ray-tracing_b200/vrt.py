@@ -139,6 +139,9 @@ class Renderer:
     def set_tuning(self, emitter_block, packed):
         self._check(self._lib.vrt_cuda_set_tuning(self._h, int(emitter_block), int(packed)), "vrt_cuda_set_tuning")
 
+    def set_band_tuning(self, ctas_per_sm):
+        self._check(self._lib.vrt_cuda_set_band_tuning(self._h, int(ctas_per_sm)), "vrt_cuda_set_band_tuning")
+
     # ---- frame ----
     @staticmethod
     def frame(view, origin, width, height, flags, tiles=(1, 1), bound_sigmas=0.0, rows=(0, 0)):

@@ -39,6 +39,8 @@
 struct __attribute__((aligned(8))) float2 { float x, y; };
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct dim3
 {
     unsigned x, y, z;

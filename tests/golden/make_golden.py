@@ -73,7 +73,7 @@ def main():
             rad[k] = Ref.radiance(scene[idx[offs[t] : offs[t + 1]]], origin, dirs[k : k + 1], variant)[0]
         out[key] = rad
     out["c1_rad_untiled_as"] = Ref.radiance(scene, origin, dirs, 1)
-    for mode in (1, 4, 5, 8):
+    for mode in (1, 2, 3, 4, 5, 6, 7, 8):
         img, _, terms = Ref.render_app(mode, scene, 256, 256, tiles=16, threads=8)
         out[f"c1_image_mode{mode}"] = img
         out[f"c1_terms_mode{mode}"] = np.array([terms])
