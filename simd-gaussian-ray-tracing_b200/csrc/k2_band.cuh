@@ -37,6 +37,7 @@ struct BandSmem
     float fmx[WIN_CAP];            // running max of front  : j < f  <=>  fmx[j] <= Smin
     float bmn[WIN_CAP];            // suffix  min of back   : j >= bk <=>  bmn[j] >= Smax
     float srem[WIN_CAP];           // suffix  min of mumin - 4 sigma: shallowest sample of the emitters j, j+1, ...
+    uint32_t acnt[WIN_CAP + 1];    // entries some lane sees among [0, j)
 };
 
 __device__ __forceinline__ int ordered_int(float x)
@@ -85,13 +86,49 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
         const uint32_t slot = args.cell_slot ? args.cell_slot[cell] : NO_SLOT;
         const uint32_t q_begin = slot != NO_SLOT ? slice * frame_slice(G) : 0u, q_end = slot != NO_SLOT ? min(n, q_begin + frame_slice(G)) : n;
 
-        // stage the whole list (occluder part) once
+        // The depth bounds of pass A are WARP-UNIFORM, and every ray of the cell lies inside the pyramid of its four corner
+        // rays: min over the lanes of mu = oc . n is bounded below by the minimum over the corner rays (the direction farthest
+        // from oc within a convex set of directions is a vertex), the maximum above by the corner maximum plus
+        // (k sigma + |oc| theta) theta + |oc| theta^2 / 2 (theta = angular diagonal of the cell; the centre of a listed Gaussian
+        // lies within k sigma of the cell's frustum, so its distance to any of the cell's rays is at most k sigma + |oc| theta).
+        // So they are computed by the lanes in parallel over the ENTRIES while staging, not by warp reductions per entry.
+        float crx[4], cry[4], crz[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+        {
+            const int src = (c & 1 ? 7 : 0) + (c & 2 ? 24 : 0);
+            crx[c] = __shfl_sync(0xffffffffu, ray.nx, src);
+            cry[c] = __shfl_sync(0xffffffffu, ray.ny, src);
+            crz[c] = __shfl_sync(0xffffffffu, ray.nz, src);
+        }
+        float theta;
+        {
+            const float dx = crx[0] - crx[3], dy = cry[0] - cry[3], dz = crz[0] - crz[3];
+            theta = sqrtf(dx * dx + dy * dy + dz * dz) * 1.0001f + 1e-7f;
+            theta = (theta == theta) ? theta : 3.0e38f; // a degenerate ray in the cell: no saturation shortcut anywhere
+        }
         __syncwarp();
         for (uint32_t j = lane; j < n; j += 32)
         {
             const Rec *r = args.rec + args.list_idx[off + j];
-            sm.a[j] = r->a;
-            sm.b[j] = r->b;
+            const float4 a = r->a, b = r->b;
+            sm.a[j] = a;
+            sm.b[j] = b;
+            float mumin = 3.0e38f, mumax = -3.0e38f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+                const float m = fmaf(a.z, crz[c], fmaf(a.y, cry[c], a.x * crx[c]));
+                mumin = fminf(mumin, m);
+                mumax = fmaxf(mumax, m);
+            }
+            const float ocn = sqrtf(fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x)));
+            mumax += (G.bound_k * b.w + 1.5f * ocn * theta) * theta * 1.0001f;
+            const float big = fmaxf(fabsf(mumax), fabsf(mumin));
+            const float half = tsat * 1.0000005f / b.x + 1e-6f * big; // t >= tsat must hold after fp32 rounding of t
+            const float margin = 2e-6f * big;                        // sign tests: a sample within a few ulp of the centre takes the signed body
+            sm.fb[j] = make_float4(mumax + half, mumin - half, mumax + margin, mumin - margin);
+            sm.smin1[j] = mumin - 4.f * b.w;
         }
         __syncwarp();
 
@@ -99,7 +136,6 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
         float C = 0.f, total = 0.f, etot = 0.f, pe = 0.f;
         uint32_t n_alive = 0;
         {
-            float fm = -3.0e38f;
             for (uint32_t j = 0; j < n; ++j)
             {
                 const float4 a = sm.a[j], b = sm.b[j];
@@ -112,25 +148,35 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                 const bool alive = __any_sync(0xffffffffu, e > args.skip_thresh);
                 const float A = alive ? w : 0.f;
                 total += A;
+                if (lane == 0) sm.acnt[j] = n_alive;
                 n_alive += alive ? 1u : 0u;
-                const float mumax = warp_max_f(mu), mumin = warp_min_f(mu);
                 // erf(-m) is saturated for an occluder more than t_sat widths beyond the origin (the usual case): same value, no erf
-                if (mumin * b.x >= tsat) C = fmaf(-A, esat, C);
+                if (sm.fb[j].w * b.x >= tsat) C = fmaf(-A, esat, C);
                 else C = fmaf(A, erf_variant<ERF>(-mu * b.x), C);
-                const float half = tsat * 1.0000005f / b.x + 1e-6f * fmaxf(fabsf(mumax), fabsf(mumin)); // t >= tsat must hold after fp32 rounding of t
-                const float front = alive ? mumax + half : -3.0e38f;
-                fm = fmaxf(fm, front);
-                if (lane == 0)
+                if (!alive && lane == 0)
                 {
-                    // the sign tests of pass B carry a depth margin: a sample within a few ulp of the centre takes the signed body
-                    const float margin = 2e-6f * fmaxf(fabsf(mumax), fabsf(mumin));
-                    sm.fb[j] = make_float4(front, alive ? mumin - half : 3.0e38f, mumax + margin, mumin - margin);
-                    sm.fmx[j] = fm;
-                    sm.smin1[j] = mumin - 4.f * b.w;
+                    sm.fb[j].x = -3.0e38f; // never blocks the saturated head ...
+                    sm.fb[j].y = 3.0e38f;  // ... nor the tail
                 }
             }
+            if (lane == 0) sm.acnt[n] = n_alive;
             __syncwarp();
-            // suffix minima, 32 entries per step from the end of the list
+            // running max of front (forwards), suffix minima of back and of the shallowest sample depth (backwards), 32 entries per step
+            float carry_f = -3.0e38f;
+            for (uint32_t j0 = 0; j0 < n; j0 += 32)
+            {
+                const uint32_t j = j0 + lane;
+                float vf = j < n ? sm.fb[j].x : -3.0e38f;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const float t = __shfl_up_sync(0xffffffffu, vf, d);
+                    if (lane >= d) vf = fmaxf(vf, t);
+                }
+                vf = fmaxf(vf, carry_f);
+                if (j < n) sm.fmx[j] = vf;
+                carry_f = __shfl_sync(0xffffffffu, vf, 31);
+            }
             float carry_b = 3.0e38f, carry_s = 3.0e38f;
             for (int j0 = (int)((n - 1) & ~31u); n && j0 >= 0; j0 -= 32)
             {
@@ -138,8 +184,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                 float vb = 3.0e38f, vs = 3.0e38f;
                 if (j < n)
                 {
-                    const float4 fbj = sm.fb[j];
-                    vb = fbj.y;
+                    vb = sm.fb[j].y;
                     vs = sm.smin1[j];
                     vs = (vs == vs) ? vs : -3.0e38f; // a NaN depth never licenses an exit
                 }
@@ -166,26 +211,24 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             __syncwarp();
         }
 
-        // per-lane weight of occluder j for the running prefix sums (0 for an entry no lane sees: `seen` counts the others)
-        auto weight_of = [&](uint32_t j, uint32_t &seen, uint32_t step) -> float {
+        // per-lane weight of occluder j for the running prefix sums (0 for an entry no lane sees)
+        auto weight_of = [&](uint32_t j) -> float {
             const float4 a = sm.a[j], b = sm.b[j];
             float mu, e;
             occluder_setup(a, b, ray, mu, e);
-            const bool alive = sm.fb[j].x > -1.0e38f;
-            seen += alive ? step : 0u;
-            return alive ? b.z * e : 0.f;
+            return sm.fb[j].x > -1.0e38f ? b.z * e : 0.f;
         };
 
         // ---- pass B ----
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
-        unsigned long long exec = 0, sat = 0, term = 0;
+        uint32_t exec = 0, sat = 0, term = 0; // per item: at most n x emitters (x 5 n_live at the flush)
         // window [f, bk) of the current block; Pf = sum_{j<f} A_j, Pb = sum_{j<bk} A_j (per lane); nf / nb count the entries
         // some lane sees among [0, f) / [0, bk).  The window moves with the blocks WITHOUT extra per-lane work in the common case:
         // an occluder that enters at the back is evaluated by the block it enters in (its weight is added to Pb there), and one
         // that leaves at the front was in the previous block's window, where the next block's shallowest sample depth was
         // already known (its weight was added to Pf there).  The explicit loops below only run at an item's first block, when
         // the window has to move backwards, or when consecutive windows do not overlap.
-        uint32_t f = 0, bk = 0, nf = 0, nb = 0;
+        uint32_t f = 0, bk = 0;
         float Pf = 0.f, Pb = 0.f;
         uint32_t exit_check_at = q_begin; // first block after which the exit test may run again (back-off after a failed test)
         // uniform sample-depth range of the emitter pair (je, je + 1 if real): [min(mumin - 4 sigma), max(mumax)]
@@ -250,33 +293,30 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             }
 
             // ---- place the window (explicit steps: rare, see above) ----
-            while (f < n && sm.fmx[f] <= Smin) { Pf += weight_of(f, nf, 1u); ++f; }
-            while (f > 0 && !(sm.fmx[f - 1] <= Smin)) { --f; Pf -= weight_of(f, nf, 0xFFFFFFFFu); }
-            while (bk > 0 && sm.bmn[bk - 1] >= Smax) { --bk; Pb -= weight_of(bk, nb, 0xFFFFFFFFu); }
-            while (bk < f) { Pb += weight_of(bk, nb, 1u); ++bk; } // (an empty window in front of f)
-            uint32_t bk_new = bk; // the tail [bk_new, n) is behind every sample of the block: a uniform scan, no per-lane work
+            while (f < n && sm.fmx[f] <= Smin) { Pf += weight_of(f); ++f; }
+            while (f > 0 && !(sm.fmx[f - 1] <= Smin)) { --f; Pf -= weight_of(f); }
+            while (bk > 0 && sm.bmn[bk - 1] >= Smax) { --bk; Pb -= weight_of(bk); }
+            while (bk < f) { Pb += weight_of(bk); ++bk; } // (an empty window in front of f)
+            // two uniform scans, no per-lane work: the tail [bk_new, n) is behind every sample of this block, and the window
+            // entries [f, f_next) will be in front of every sample of the next one
+            uint32_t bk_new = bk;
             while (bk_new < n && !(sm.bmn[bk_new] >= Smax)) ++bk_new;
+            uint32_t f_next = f;
+            while (f_next < bk_new && sm.fmx[f_next] <= Smin_next) ++f_next;
 
             const float Pf_now = Pf;
-            const uint32_t f_now = f, nf_now = nf;
+            const uint32_t f_now = f;
             float base0 = 0.f, base1 = 0.f;
-            bool leaving = true; // j == f so far: the leading run of the NEXT block can still grow
             for (uint32_t j = f_now; j < bk_new; ++j)
             {
                 const float4 fbj = sm.fb[j];
-                const bool seen = fbj.x > -1.0e38f;
-                leaving = leaving && sm.fmx[j] <= Smin_next;
-                if (!seen) // no lane sees it: weight 0 everywhere
-                {
-                    if (leaving) f = j + 1;
-                    continue;
-                }
+                if (!(fbj.x > -1.0e38f)) continue; // no lane sees it: weight 0 everywhere
                 const float4 a = sm.a[j], b = sm.b[j];
                 float mu, e;
                 occluder_setup(a, b, ray, mu, e);
                 const float A = b.z * e, r = b.x, nm = -(mu - s0) * r;
-                if (j >= bk) { Pb += A; ++nb; }                 // enters the window at the back
-                if (leaving) { Pf += A; ++nf; f = j + 1; }       // in front of every sample of the next block
+                if (j >= bk) Pb += A;     // enters the window at the back
+                if (j < f_next) Pf += A;  // leaves it at the front after this block
                 const float2 rr = make_float2(r, r), mm = make_float2(nm, nm);
 #pragma unroll
                 for (int g = 0; g < 2; ++g)
@@ -320,11 +360,12 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                 }
             }
             bk = bk_new;
+            f = f_next;
             // head [0, f_now) in front of every sample, tail [bk, n) behind: resolved by the two prefix sums
             const float base_common = esat * (Pf_now - (total - Pb));
             base0 += base_common;
             base1 += base_common;
-            sat += (unsigned long long)(nf_now + (n_alive - nb)) * n_real;
+            sat += (sm.acnt[f_now] + (n_alive - sm.acnt[bk])) * n_real;
             // T(s) = 2^(C - base - acc); pdf at the samples = c_bar e^{-k^2/2}, k = -4..0 (src/vrt/rt.h:153-161)
             float lt_max = -3.0e38f; // log2 T at the block's least occluded sample (k = -4 of every emitter)
 #pragma unroll
@@ -364,7 +405,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                     }
                     if (__all_sync(0xffffffffu, ex2_approx(lt) * w_rem <= TERMINATE_EPS))
                     {
-                        term += (unsigned long long)(q_end - (q0 + Q)) * n_alive;
+                        term += (q_end - (q0 + Q)) * n_alive;
                         break;
                     }
                     exit_check_at = q0 + 3 * Q; // not yet: look again two blocks further on
@@ -373,8 +414,8 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
         }
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
         else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
-        if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
-        if (lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
-        if (lane == 0 && term) atomicAdd(args.terms_term, term * 5ull * n_live);
+        if (lane == 0 && exec) atomicAdd(args.terms_exec, (unsigned long long)exec * 5ull * n_live);
+        if (lane == 0 && sat) atomicAdd(args.terms_sat, (unsigned long long)sat * 5ull * n_live);
+        if (lane == 0 && term) atomicAdd(args.terms_term, (unsigned long long)term * 5ull * n_live);
     }
 }

@@ -644,7 +644,7 @@ static void pin_host(vrt_cuda_ctx *ctx, const void *p, size_t bytes)
     }
     // registration covers whole pages
     const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
-    if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable) == cudaSuccess)
+    if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess)
     {
         slot.ptr = (void *)lo;
         slot.bytes = hi - lo;
@@ -676,7 +676,7 @@ int vrt_cuda_pin_buffer(vrt_cuda_ctx *ctx, void *p, uint64_t bytes)
     if (!p || !bytes) return fail(ctx, VRT_CUDA_E_INVALID, "nothing to pin");
     CU(cudaSetDevice(ctx->device));
     const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
-    CU(cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable));
+    CU(cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return 0;
 }
 
@@ -1380,13 +1380,35 @@ static int render_host(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t 
     if (!frame) return fail(ctx, VRT_CUDA_E_INVALID, "frame is NULL");
     CU(cudaSetDevice(ctx->device));
     const size_t npix = (size_t)frame->width * frame->height;
+    // A page-locked, mapped caller buffer (vrt_cuda_set_host_pinning / vrt_cuda_pin_buffer) is written by the render kernel
+    // itself: K3's 16-byte stores go straight over PCIe while the frame is still being computed, and no copy-back remains.
+    // Anything else is rendered into a device buffer and copied (staged by the driver when the memory is pageable).
+    uint32_t *image_target = nullptr;
+    float *rad_target = nullptr;
     if (image)
-        if (int rc = reserve(ctx, ctx->out_image, npix * sizeof(uint32_t))) return rc;
+    {
+        pin_host(ctx, image, npix * sizeof(uint32_t));
+        void *d = nullptr;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, image) == cudaSuccess && at.type == cudaMemoryTypeHost && cudaHostGetDevicePointer(&d, image, 0) == cudaSuccess) image_target = (uint32_t *)d;
+        else cudaGetLastError();
+        if (!image_target)
+            if (int rc = reserve(ctx, ctx->out_image, npix * sizeof(uint32_t))) return rc;
+    }
     if (radiance)
-        if (int rc = reserve(ctx, ctx->out_rad, npix * sizeof(float) * 4)) return rc;
+    {
+        pin_host(ctx, radiance, npix * sizeof(float) * 4);
+        void *d = nullptr;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, radiance) == cudaSuccess && at.type == cudaMemoryTypeHost && cudaHostGetDevicePointer(&d, radiance, 0) == cudaSuccess) rad_target = (float *)d;
+        else cudaGetLastError();
+        if (!rad_target)
+            if (int rc = reserve(ctx, ctx->out_rad, npix * sizeof(float) * 4)) return rc;
+    }
     if (running && !*running) return VRT_CUDA_INTERRUPTED;
     // with a `running` flag the statistics are read after the poll loop, not inside render_device (which would block)
-    int rc = vrt_cuda_render_device(ctx, frame, image ? (uint32_t *)ctx->out_image.p : nullptr, radiance ? (float *)ctx->out_rad.p : nullptr, running ? nullptr : stats);
+    int rc = vrt_cuda_render_device(ctx, frame, image ? (image_target ? image_target : (uint32_t *)ctx->out_image.p) : nullptr,
+                                    radiance ? (rad_target ? rad_target : (float *)ctx->out_rad.p) : nullptr, running ? nullptr : stats);
     if (rc) return rc;
     bool interrupted = false;
     if (running)
@@ -1410,10 +1432,8 @@ static int render_host(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t 
     }
     const FrameGeom &G = ctx->geom;
     const size_t row0 = (size_t)G.row_begin, rows = (size_t)(G.row_end - G.row_begin);
-    if (image) pin_host(ctx, image + row0 * G.W, rows * G.W * sizeof(uint32_t));
-    if (radiance) pin_host(ctx, radiance + row0 * G.W * 4, rows * G.W * sizeof(float) * 4);
-    if (image) CU(cudaMemcpyAsync(image + row0 * G.W, (uint32_t *)ctx->out_image.p + row0 * G.W, rows * G.W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (radiance) CU(cudaMemcpyAsync(radiance + row0 * G.W * 4, (float *)ctx->out_rad.p + row0 * G.W * 4, rows * G.W * sizeof(float) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (image && !image_target) CU(cudaMemcpyAsync(image + row0 * G.W, (uint32_t *)ctx->out_image.p + row0 * G.W, rows * G.W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (radiance && !rad_target) CU(cudaMemcpyAsync(radiance + row0 * G.W * 4, (float *)ctx->out_rad.p + row0 * G.W * 4, rows * G.W * sizeof(float) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -279,7 +279,7 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 // mapped / registered host memory: host and "device" share one address space here, so these are bookkeeping only
 enum { cudaErrorNotReady = 600 };
-enum { cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0, cudaHostRegisterPortable = 1 };
+enum { cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0, cudaHostRegisterPortable = 1, cudaHostRegisterMapped = 2 };
 static inline cudaError_t cudaMemset(void *p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
 struct cudaPointerAttributes { cudaMemoryType type; };

@@ -25,7 +25,7 @@ def test_cuda_library_exports_every_declared_symbol(pkg):
     for sym in declared:
         assert hasattr(lib, sym), f"libvrt_cuda.so does not export {sym}"
     assert sorted(pkg._ffi.CUDA_SYMBOLS) == declared
-    assert lib.vrt_cuda_abi_version() == 4
+    assert lib.vrt_cuda_abi_version() == 5
 
 
 def test_host_library_exports_every_declared_symbol(pkg):
@@ -49,7 +49,7 @@ def test_struct_layouts_match_header(pkg):
     import ctypes
 
     assert ctypes.sizeof(pkg._ffi.Frame) == 16 * 4 + 4 * 4 + 8 * 4
-    assert ctypes.sizeof(pkg._ffi.Stats) == 3 * 8 + 2 * 4 + 2 * 8 + 4 * 4 + 8
+    assert ctypes.sizeof(pkg._ffi.Stats) == 3 * 8 + 2 * 4 + 2 * 8 + 4 * 4 + 8 + 8  # ... + terms_saturated + terms_terminated
 
 
 def test_python_flag_values_match_header(pkg):
