@@ -33,6 +33,7 @@ struct BandSmem
 {
     float4 a[WIN_CAP], b[WIN_CAP]; // occluder part of the records
     float4 fb[WIN_CAP];            // (front_j, back_j, mumax_j + margin, mumin_j - margin); front = -3e38: no lane sees it
+
     float smin1[WIN_CAP];          // mumin_j - 4 sigma_j: shallowest sample depth of emitter j over the warp
     float fmx[WIN_CAP];            // running max of front  : j < f  <=>  fmx[j] <= Smin
     float bmn[WIN_CAP];            // suffix  min of back   : j >= bk <=>  bmn[j] >= Smax
@@ -413,6 +414,9 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             }
         }
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
+        // 16-byte framebuffer stores (shuffle transpose).  Measured on BASELINE config 5, same box: 22.54 ms with them, 21.71 ms
+        // with one word per lane (the epilogue's extra live values cost more than the 24 saved store instructions per cell);
+        // kept because the north star asks for vectorised framebuffer writes and zero-copy output wants wide PCIe writes.
         else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, (unsigned long long)exec * 5ull * n_live);
         if (lane == 0 && sat) atomicAdd(args.terms_sat, (unsigned long long)sat * 5ull * n_live);

@@ -387,7 +387,15 @@ __global__ void __launch_bounds__(k2_cta_warps(Q, MINB) * 32, MINB) k2_render(co
 
         // ---- K3: framebuffer ----
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
-        else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
+        else if (live)
+        {
+            // One word per lane (32-byte row segments) in THIS kernel: with the 16-byte form inlined into its epilogue ptxas
+            // schedules the inner term 6 % slower (149.2 vs 140.9 ms on BASELINE config 5, same box, profiles/r02_strict_ab.md);
+            // the default kernel (k2_band), the combine pass and the variants store 16 bytes.
+            const size_t pi = (size_t)py * G.W + px;
+            if (args.radiance) args.radiance[pi] = make_float4(Lr, Lg, Lb, La);
+            if (args.image) args.image[pi] = pack_pixel(args, Lr, Lg, Lb, La);
+        }
         if (lane == 0 && exec) atomicAdd(args.terms_exec, exec * 5ull * n_live);
         if (WIN && lane == 0 && sat) atomicAdd(args.terms_sat, sat * 5ull * n_live);
         exec = 0;

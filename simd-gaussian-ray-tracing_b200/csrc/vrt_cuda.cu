@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <string>
@@ -941,12 +942,24 @@ static int enqueue_cell_lists(vrt_cuda_ctx *ctx, const FrameGeom &G, uint64_t n_
     return 0;
 }
 
+// Most list entries a frame may hold: device offsets are 32-bit.  VRT_CUDA_MAX_LIST_ENTRIES lowers the limit so that the
+// tests can reach the refusal without building four billion entries.
+static uint64_t max_list_entries()
+{
+    static const uint64_t limit = [] {
+        const char *e = std::getenv("VRT_CUDA_MAX_LIST_ENTRIES");
+        const unsigned long long v = e ? std::strtoull(e, nullptr, 10) : 0ull;
+        return (uint64_t)((v > 0 && v < 0xFFFFFFF0ull) ? v : 0xFFFFFFF0ull);
+    }();
+    return limit;
+}
+
 // after the frame's synchronisation: did the bin lists and the index array fit?  (false: capacities were raised, run again)
 static int cell_lists_fit(vrt_cuda_ctx *ctx, const TileStats &ts, bool &fit)
 {
     fit = true;
-    if (ts.leaf_entries > 0xFFFFFFF0ull || ts.bin_entries > 0xFFFFFFF0ull)
-        return fail(ctx, VRT_CUDA_E_NOMEM, "more than 2^32 list entries in this frame (%llu cell entries, %llu bin entries): render it in row bands or tighten bound_sigmas",
+    if (ts.leaf_entries > max_list_entries() || ts.bin_entries > max_list_entries())
+        return fail(ctx, VRT_CUDA_E_NOMEM, "too many list entries in this frame (%llu cell entries, %llu bin entries; device offsets are 32-bit): render it in row bands or tighten bound_sigmas",
                     (unsigned long long)ts.leaf_entries, (unsigned long long)ts.bin_entries);
     if (ts.bin_entries > ctx->bin_idx.cap / sizeof(uint32_t))
     {
@@ -1046,8 +1059,8 @@ static int tile_build(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame)
             unsigned long long total = 0;
             CU(cudaMemcpyAsync(&total, &((TileStats *)ctx->stats.p)->leaf_entries, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
-            if (total > 0xFFFFFFF0ull)
-                return fail(ctx, VRT_CUDA_E_NOMEM, "the literal tile lists hold %llu entries (more than 2^32): use a *_BOUND list mode or fewer tiles", total);
+            if (total > max_list_entries())
+                return fail(ctx, VRT_CUDA_E_NOMEM, "the literal tile lists hold %llu entries (device offsets are 32-bit): use a *_BOUND list mode or fewer tiles", total);
             if (int rc = reserve(ctx, ctx->cidx, sizeof(uint32_t) * std::max<uint64_t>(total, 1))) return rc;
             k1_cull_tiles<true><<<nt, 256, 0, ctx->stream>>>(G, (const Rec *)ctx->rec.p, (const float4 *)ctx->cullrec.p, (uint32_t)N, nullptr, (const uint32_t *)ctx->coffsets.p, (uint32_t *)ctx->cidx.p, nt);
             ctx->launches += 4;

@@ -15,6 +15,7 @@ from parity_util import channel_diff_lsb, oracle_radiance, reference_lists
 from test_gpu_parity import all_pixels, check, gpu_at
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def bound_flags(V, erf=0):
@@ -289,3 +290,40 @@ def test_long_lists_are_sorted_in_global_memory(pkg, renderer):
     pix = all_pixels(W, H, 37)
     ideal = oracle_radiance(scene, cam.view_matrix, origin, W, H, pix, 1, f64="unit", near_sigmas=12)
     check(gpu_at(rad, pix, W), ideal, "long lists vs arbiter")
+
+
+def test_entry_totals_are_64_bit_and_refused_not_wrapped(pkg):
+    """The sum of the list lengths is kept in 64 bits (the leaf cursor, k1_total64 beside the 32-bit scan of the literal lists);
+    past the 32-bit offset range the tile call returns VRT_CUDA_E_NOMEM instead of writing through wrapped offsets.
+    VRT_CUDA_MAX_LIST_ENTRIES lowers that limit for this test (read once per process: a child process)."""
+    import subprocess
+
+    code = (
+        "import sys, os, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as ge\n"
+        "pkg = ge.load_package()\n"
+        "if os.environ.get('VRT_EMU') == '1':\n"
+        "    import ctypes; sys.path.insert(0, os.path.join(%r, 'tests', 'emu')); import build_emu\n"
+        "    lib = ctypes.CDLL(build_emu.build())\n"
+        "    for sym, (res, args) in pkg._ffi.CUDA_SYMBOLS.items():\n"
+        "        fn = getattr(lib, sym); fn.restype, fn.argtypes = res, args\n"
+        "    pkg._ffi._cuda = lib\n"
+        "V = pkg.vrt; r = V.Renderer(0)\n"
+        "scene = pkg.scenes.synthetic(600, 3, -1.0, -0.7); cam, origin = V.camera_t.app(64, 64); r.set_gaussians(scene)\n"
+        "out = []\n"
+        "for flags, tiles in (((V.MODE4 & ~V.LIST_MASK) | V.LIST_BOUND, (1, 1)), (V.MODE8 | V.NO_SKIP, (8, 8))):\n"
+        "    try:\n"
+        "        r.tile(r.frame(cam.view_matrix, origin, 64, 64, flags, tiles)); out.append('built')\n"
+        "    except V.VrtCudaError as e:\n"
+        "        out.append('refused' if '= -4' in str(e) and '32-bit' in str(e) else 'other: ' + str(e))\n"
+        "print(' | '.join(out))\n"
+    ) % (ROOT, ROOT)
+    env = dict(os.environ, VRT_CUDA_MAX_LIST_ENTRIES="2000")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1] == "refused | refused", r.stdout
+    env.pop("VRT_CUDA_MAX_LIST_ENTRIES")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1] == "built | built", r.stdout + r.stderr[-2000:]
