@@ -32,6 +32,7 @@ constexpr float TERMINATE_EPS = 1e-6f; // bound on the per-channel radiance drop
 struct BandSmem
 {
     float4 a[WIN_CAP], b[WIN_CAP]; // occluder part of the records
+    float4 c[WIN_CAP];             // albedo (read at a block's epilogue: keeps 16 registers free during the window walk)
     float4 fb[WIN_CAP];            // (front_j, back_j, mumax_j + margin, mumin_j - margin); front = -3e38: no lane sees it
 
     float smin1[WIN_CAP];          // mumin_j - 4 sigma_j: shallowest sample depth of emitter j over the warp
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             const float4 a = r->a, b = r->b;
             sm.a[j] = a;
             sm.b[j] = b;
+            sm.c[j] = r->c;
             float mumin = 3.0e38f, mumax = -3.0e38f;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -246,7 +248,6 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
         {
             const uint32_t n_real = min((uint32_t)Q, q_end - q0);
             float s[Q][5], acc[Q][5], wgt[Q];
-            float4 alb[Q];
             // one depth shift per block keeps s r - m small (uniform: the first emitter's shallowest centre depth)
             float s0 = sm.fb[q0].w;
             s0 = (fabsf(s0) <= 3.0e38f) ? s0 : 0.f;
@@ -257,7 +258,6 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                 const bool real = (uint32_t)e < n_real;
                 const uint32_t je = real ? q0 + e : q0;
                 const float4 a = sm.a[je], b = sm.b[je];
-                alb[e] = args.rec[args.list_idx[off + je]].c;
                 float mu, ee;
                 occluder_setup(a, b, ray, mu, ee);
                 const float w = b.z * ee;
@@ -300,10 +300,20 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             while (bk < f) { Pb += weight_of(bk); ++bk; } // (an empty window in front of f)
             // two uniform scans, no per-lane work: the tail [bk_new, n) is behind every sample of this block, and the window
             // entries [f, f_next) will be in front of every sample of the next one
-            uint32_t bk_new = bk;
-            while (bk_new < n && !(sm.bmn[bk_new] >= Smax)) ++bk_new;
-            uint32_t f_next = f;
-            while (f_next < bk_new && sm.fmx[f_next] <= Smin_next) ++f_next;
+            // (32 entries per step, one per lane: a window rarely spans more)
+            uint32_t bk_new = bk, f_next = f;
+            for (;; bk_new += 32)
+            {
+                const uint32_t j = bk_new + lane;
+                const uint32_t m = __ballot_sync(0xffffffffu, j >= n || sm.bmn[j] >= Smax);
+                if (m) { bk_new += __ffs(m) - 1; break; }
+            }
+            for (;; f_next += 32)
+            {
+                const uint32_t j = f_next + lane;
+                const uint32_t m = __ballot_sync(0xffffffffu, j >= bk_new || !(sm.fmx[j] <= Smin_next));
+                if (m) { f_next += __ffs(m) - 1; break; }
+            }
 
             const float Pf_now = Pf;
             const uint32_t f_now = f;
@@ -380,10 +390,11 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                 inner = fmaf(6.0653065971263342e-1f, ex2_approx(Cb - acc[e][3]), inner);
                 inner += ex2_approx(Cb - acc[e][4]);
                 inner *= wgt[e];
-                Lr = fmaf(alb[e].x, inner, Lr);
-                Lg = fmaf(alb[e].y, inner, Lg);
-                Lb = fmaf(alb[e].z, inner, Lb);
-                La = fmaf(alb[e].w, inner, La);
+                const float4 al = sm.c[(uint32_t)e < n_real ? q0 + e : q0];
+                Lr = fmaf(al.x, inner, Lr);
+                Lg = fmaf(al.y, inner, Lg);
+                Lb = fmaf(al.z, inner, Lb);
+                La = fmaf(al.w, inner, La);
                 if ((uint32_t)e < n_real) lt_max = fmaxf(lt_max, l0);
             }
             // ---- early termination: nothing behind can add more than TERMINATE_EPS to any channel ----
