@@ -226,6 +226,18 @@ int vrt_cuda_set_host_pinning(vrt_cuda_ctx *ctx, int on);
 int vrt_cuda_pin_buffer(vrt_cuda_ctx *ctx, void *p, uint64_t bytes);
 int vrt_cuda_unpin_buffer(vrt_cuda_ctx *ctx, void *p);
 
+/* Multi-GPU output without a gather step (one process per GPU).  The rank that owns the frame allocates the image on its GPU
+ * with vrt_cuda_peer_image_create and hands the 64-byte handle to the other processes (any byte transport); they map it with
+ * vrt_cuda_peer_image_open and pass the mapped pointer as `image_dev` of vrt_cuda_render_device.  K3's 16-byte stores of a rank's
+ * row band then go straight into the owner's memory over NVLink / NVSwitch while the band is still being computed: the transfer
+ * is part of the render kernel, and what remains of the exchange is one barrier.  (The reference composes its tiles into the
+ * caller's image with a copy loop after each tile, rt.h:388-399; this is the same step across GPUs.)  _close unmaps an imported
+ * image or frees an owned one.  An image can be opened once per importing process; not within the process that created it. */
+#define VRT_CUDA_PEER_HANDLE_BYTES 64
+int vrt_cuda_peer_image_create(vrt_cuda_ctx *ctx, uint64_t bytes, void **image_dev_out, unsigned char *handle_out);
+int vrt_cuda_peer_image_open(vrt_cuda_ctx *ctx, const unsigned char *handle, void **image_dev_out);
+int vrt_cuda_peer_image_close(vrt_cuda_ctx *ctx, void *image_dev);
+
 /* vrt_cuda_tile + vrt_cuda_render in one call: one iteration of the app's frame loop (main.cpp:257-297). */
 int vrt_cuda_frame_render(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t *image, float *radiance,
                           vrt_cuda_stats *stats);

@@ -73,6 +73,9 @@ CUDA_SYMBOLS = {
     "vrt_cuda_set_host_pinning": (c_i, [vp, c_i]),
     "vrt_cuda_pin_buffer": (c_i, [vp, vp, c_u64]),
     "vrt_cuda_unpin_buffer": (c_i, [vp, vp]),
+    "vrt_cuda_peer_image_create": (c_i, [vp, c_u64, ctypes.POINTER(vp), vp]),
+    "vrt_cuda_peer_image_open": (c_i, [vp, vp, ctypes.POINTER(vp)]),
+    "vrt_cuda_peer_image_close": (c_i, [vp, vp]),
     "vrt_cuda_row_costs": (c_i, [vp, vp, c_u32, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32)]),
     "vrt_cuda_set_tuning": (c_i, [vp, c_i, c_i]),
     "vrt_cuda_set_band_tuning": (c_i, [vp, c_i]),

@@ -75,3 +75,54 @@ def gather_bands(image, bounds, rank, world, dist):
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+class PeerImage:
+    """The frame buffer of a multi-GPU frame: ONE image on rank 0's GPU that every rank's render kernel stores its row band
+    into directly (vrt_cuda_peer_image_create / _open: CUDA IPC, peer stores over NVLink / NVSwitch), so the exchange step of a
+    frame shrinks from a gather of the bands to one barrier (`complete`).  `ok` is False on every rank when any rank could not
+    map the image (no peer access between the GPUs, or a CPU test backend): the caller then keeps the gather path."""
+
+    def __init__(self, renderer, height, width, rank, world, dist, torch):
+        self.renderer, self.rank, self.dist, self.torch = renderer, rank, dist, torch
+        self.ptr, self.ok, self.why = 0, True, ""
+        handle = [None]
+        if rank == 0:
+            try:
+                self.ptr, handle[0] = renderer.peer_image_create(height * width * 4)
+            except RuntimeError as exc:
+                self.ok, self.why = False, str(exc)
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            try:
+                if handle[0] is None:
+                    raise RuntimeError("the owner could not create the image")
+                self.ptr = renderer.peer_image_open(handle[0])
+            except RuntimeError as exc:
+                self.ok, self.why = False, str(exc)
+        dev = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        flag = torch.tensor([1.0 if self.ok else 0.0], dtype=torch.float32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        everyone = bool(flag.item() > 0.5)
+        if not everyone and self.ptr:
+            renderer.peer_image_close(self.ptr)
+            self.ptr = 0
+        self.ok = everyone
+        self._token = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.tensor = None
+        if self.ok and rank == 0:
+            class _Raw:  # rank 0's view of its own allocation as a [H, W] int32 tensor
+                __cuda_array_interface__ = {"shape": (height, width), "typestr": "<i4", "data": (self.ptr, False), "version": 2}
+
+            self.tensor = torch.as_tensor(_Raw(), device=dev)
+
+    def complete(self):
+        """Enqueue the frame's barrier on the current stream: once it has passed on rank 0, every rank's render kernel has
+        finished and its stores have landed in rank 0's memory."""
+        self.dist.all_reduce(self._token)
+
+    def close(self):
+        self.tensor = None
+        if self.ptr:
+            self.renderer.peer_image_close(self.ptr)
+            self.ptr = 0

@@ -90,6 +90,8 @@ struct vrt_cuda_ctx
     int pinned_next = 0;
     int pin_mode = 0; // opt-in (vrt_cuda_set_host_pinning): the caller promises its buffers outlive the registration
     DevBuf out_image, out_rad;
+    struct PeerImage { void *ptr = nullptr; bool owned = false; };
+    std::vector<PeerImage> peer_images; // vrt_cuda_peer_image_create / _open
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
     DevBuf tile_off;
     DevBuf lit_offsets, lit_counts, lit_idx; // literal lists (tile_gaussians membership) kept for vrt_cuda_get_lists while K2 uses the visible lists
@@ -566,6 +568,11 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &r : ctx->pinned)
         if (r.ptr) cudaHostUnregister(r.ptr);
+    for (auto &pi : ctx->peer_images)
+    {
+        if (pi.owned) cudaFree(pi.ptr);
+        else cudaIpcCloseMemHandle(pi.ptr);
+    }
     if (ctx->abort_stream) { cudaStreamSynchronize(ctx->abort_stream); cudaStreamDestroy(ctx->abort_stream); }
     if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
     if (ctx->abort_dev) cudaFree(ctx->abort_dev);
@@ -688,6 +695,71 @@ int vrt_cuda_unpin_buffer(vrt_cuda_ctx *ctx, void *p)
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaHostUnregister((void *)((uintptr_t)p & ~(uintptr_t)4095)));
     return 0;
+}
+
+// ---- peer images: a frame buffer on one GPU that the other ranks' render kernels store into (CUDA IPC over NVLink) ----
+static_assert(sizeof(cudaIpcMemHandle_t) == VRT_CUDA_PEER_HANDLE_BYTES, "handle size");
+
+int vrt_cuda_peer_image_create(vrt_cuda_ctx *ctx, uint64_t bytes, void **image_dev_out, unsigned char *handle_out)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!bytes || !image_dev_out || !handle_out) return fail(ctx, VRT_CUDA_E_INVALID, "peer image: size, pointer and handle are required");
+    CU(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    // an allocation of its own (not a slice of a pool): the handle names a whole cudaMalloc block
+    if (cudaMalloc(&p, bytes) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return fail(ctx, VRT_CUDA_E_NOMEM, "peer image: cannot allocate %llu bytes", (unsigned long long)bytes);
+    }
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        cudaFree(p);
+        return fail(ctx, VRT_CUDA_E_CUDA, "peer image: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, sizeof(h));
+    ctx->peer_images.push_back({p, true});
+    *image_dev_out = p;
+    return 0;
+}
+
+int vrt_cuda_peer_image_open(vrt_cuda_ctx *ctx, const unsigned char *handle, void **image_dev_out)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    if (!handle || !image_dev_out) return fail(ctx, VRT_CUDA_E_INVALID, "peer image: handle and pointer are required");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        return fail(ctx, VRT_CUDA_E_CUDA, "peer image: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    ctx->peer_images.push_back({p, false});
+    *image_dev_out = p;
+    return 0;
+}
+
+int vrt_cuda_peer_image_close(vrt_cuda_ctx *ctx, void *image_dev)
+{
+    if (!ctx) return VRT_CUDA_E_INVALID;
+    for (size_t i = 0; i < ctx->peer_images.size(); ++i)
+        if (ctx->peer_images[i].ptr == image_dev)
+        {
+            CU(cudaSetDevice(ctx->device));
+            CU(cudaStreamSynchronize(ctx->stream));
+            const bool owned = ctx->peer_images[i].owned;
+            ctx->peer_images.erase(ctx->peer_images.begin() + (long)i);
+            if (owned) CU(cudaFree(image_dev));
+            else CU(cudaIpcCloseMemHandle(image_dev));
+            return 0;
+        }
+    return fail(ctx, VRT_CUDA_E_INVALID, "peer image: not an image of this context");
 }
 
 int vrt_cuda_abort(vrt_cuda_ctx *ctx, int on)

@@ -219,6 +219,22 @@ class Renderer:
     def unpin_buffer(self, array):
         self._check(self._lib.vrt_cuda_unpin_buffer(self._h, _ptr(array)), "vrt_cuda_unpin_buffer")
 
+    # multi-GPU output without a gather: a frame buffer on one GPU that other processes' render kernels store into
+    def peer_image_create(self, nbytes):
+        """(device pointer, 64-byte handle) of a new image on this context's GPU (vrt_cuda_peer_image_create)."""
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        self._check(self._lib.vrt_cuda_peer_image_create(self._h, int(nbytes), ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p)), "vrt_cuda_peer_image_create")
+        return int(ptr.value), bytes(handle)
+
+    def peer_image_open(self, handle):
+        """device pointer, valid on this context's GPU, of an image another process created (vrt_cuda_peer_image_open)."""
+        ptr, buf = ctypes.c_void_p(), (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.vrt_cuda_peer_image_open(self._h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ptr)), "vrt_cuda_peer_image_open")
+        return int(ptr.value)
+
+    def peer_image_close(self, ptr):
+        self._check(self._lib.vrt_cuda_peer_image_close(self._h, ctypes.c_void_p(ptr)), "vrt_cuda_peer_image_close")
+
     def render_device(self, frame, image_ptr, radiance_ptr=0, want_stats=False):
         st = Stats() if want_stats else None
         self._check(self._lib.vrt_cuda_render_device(self._h, ctypes.byref(frame), ctypes.c_void_p(int(image_ptr)) if image_ptr else None,

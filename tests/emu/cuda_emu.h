@@ -289,6 +289,12 @@ static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) 
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
+// CUDA IPC (peer images): one process, one address space here -- exporting works, importing is refused
+enum { cudaErrorNotSupported = 801, cudaIpcMemLazyEnablePeerAccess = 1 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; } // kernels complete inside their launch
 template <class T>
 static inline cudaError_t cudaMemcpyToSymbolAsync(T &symbol, const void *src, size_t n, size_t offset, cudaMemcpyKind, cudaStream_t)
