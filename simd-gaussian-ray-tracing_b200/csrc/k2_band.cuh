@@ -39,7 +39,6 @@ struct BandSmem
     float fmx[WIN_CAP];            // running max of front  : j < f  <=>  fmx[j] <= Smin
     float bmn[WIN_CAP];            // suffix  min of back   : j >= bk <=>  bmn[j] >= Smax
     float srem[WIN_CAP];           // suffix  min of mumin - 4 sigma: shallowest sample of the emitters j, j+1, ...
-    uint32_t acnt[WIN_CAP + 1];    // entries some lane sees among [0, j)
 };
 
 __device__ __forceinline__ int ordered_int(float x)
@@ -151,7 +150,6 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                 const bool alive = __any_sync(0xffffffffu, e > args.skip_thresh);
                 const float A = alive ? w : 0.f;
                 total += A;
-                if (lane == 0) sm.acnt[j] = n_alive;
                 n_alive += alive ? 1u : 0u;
                 // erf(-m) is saturated for an occluder more than t_sat widths beyond the origin (the usual case): same value, no erf
                 if (sm.fb[j].w * b.x >= tsat) C = fmaf(-A, esat, C);
@@ -162,7 +160,6 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                     sm.fb[j].y = 3.0e38f;  // ... nor the tail
                 }
             }
-            if (lane == 0) sm.acnt[n] = n_alive;
             __syncwarp();
             // running max of front (forwards), suffix minima of back and of the shallowest sample depth (backwards), 32 entries per step
             float carry_f = -3.0e38f;
@@ -336,8 +333,8 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
                     const float sming = smin_g[g], smaxg = smax_g[g];
                     float &base = g == 0 ? base0 : base1;
                     const uint32_t ng = g == 0 ? ng0 : ng1;
-                    if (fbj.x <= sming) { base = fmaf(A, esat, base); sat += ng; continue; }  // in front of every sample: erf = +esat
-                    if (fbj.y >= smaxg) { base = fmaf(-A, esat, base); sat += ng; continue; } // behind every sample: -esat
+                    if (fbj.x <= sming) { base = fmaf(A, esat, base); continue; }  // in front of every sample: erf = +esat
+                    if (fbj.y >= smaxg) { base = fmaf(-A, esat, base); continue; } // behind every sample: -esat
                     exec += ng;
                     const bool pos = fbj.z <= sming; // every sample behind the centre for every lane: t >= 0
                     const bool neg = fbj.w >= smaxg; // every sample in front of it: t <= 0
@@ -376,7 +373,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             const float base_common = esat * (Pf_now - (total - Pb));
             base0 += base_common;
             base1 += base_common;
-            sat += (sm.acnt[f_now] + (n_alive - sm.acnt[bk])) * n_real;
+            sat += n_alive * n_real; // every entry some lane sees is, for each emitter of the block, either evaluated or saturated (exec is subtracted at the flush)
             // T(s) = 2^(C - base - acc); pdf at the samples = c_bar e^{-k^2/2}, k = -4..0 (src/vrt/rt.h:153-161)
             float lt_max = -3.0e38f; // log2 T at the block's least occluded sample (k = -4 of every emitter)
 #pragma unroll
@@ -430,7 +427,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
         // kept because the north star asks for vectorised framebuffer writes and zero-copy output wants wide PCIe writes.
         else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, (unsigned long long)exec * 5ull * n_live);
-        if (lane == 0 && sat) atomicAdd(args.terms_sat, (unsigned long long)sat * 5ull * n_live);
+        if (lane == 0 && sat > exec) atomicAdd(args.terms_sat, (unsigned long long)(sat - exec) * 5ull * n_live);
         if (lane == 0 && term) atomicAdd(args.terms_term, (unsigned long long)term * 5ull * n_live);
     }
 }

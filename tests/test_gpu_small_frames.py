@@ -86,7 +86,7 @@ def test_early_exit_on_an_opaque_scene(pkg, renderer):
 
 
 def test_depth_window_long_lists_take_the_in_loop_test(pkg, renderer):
-    """Lists longer than the banded kernel's per-warp cache (160 entries) go to k2_render's in-loop saturation test; a frame
+    """Lists longer than the banded kernel's per-warp cache (152 entries) go to k2_render's in-loop saturation test; a frame
     that mixes both kinds must still be the image of the full evaluation."""
     V = pkg.vrt
     W = 32
