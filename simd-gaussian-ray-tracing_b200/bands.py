@@ -110,7 +110,7 @@ class PeerImage:
         self.ok = everyone
         self._token = torch.zeros(1, dtype=torch.float32, device=dev)
         self.tensor = None
-        if self.ok and rank == 0:
+        if self.ok and rank == 0 and dev.type == "cuda":
             class _Raw:  # rank 0's view of its own allocation as a [H, W] int32 tensor
                 __cuda_array_interface__ = {"shape": (height, width), "typestr": "<i4", "data": (self.ptr, False), "version": 2}
 

@@ -102,3 +102,67 @@ def test_rebalance_feedback_converges(pkg):
     t2 = measure(bounds)
     assert max(t0) / np.mean(t0) > 1.08
     assert max(t2) / np.mean(t2) < 1.03, (max(t2) / np.mean(t2), bounds)
+
+
+class _StandInRenderer:
+    """The three peer-image calls of vrt.Renderer with host bookkeeping only (the protocol around them is what is tested here;
+    the calls themselves run against real devices in tests/test_gpu_peer.py and under bench.py --gpus N)."""
+
+    def __init__(self, rank, fail_open_on):
+        self.rank, self.fail_open_on, self.closed = rank, fail_open_on, []
+
+    def peer_image_create(self, nbytes):
+        return 0x1000, bytes(range(64))
+
+    def peer_image_open(self, handle):
+        if self.rank == self.fail_open_on:
+            raise RuntimeError("peer image: cudaIpcOpenMemHandle: peer access is not supported between these two devices")
+        assert handle == bytes(range(64))
+        return 0x2000 + self.rank
+
+    def peer_image_close(self, ptr):
+        self.closed.append(ptr)
+
+
+def _peer_worker(rank, world, port, fail_open_on, result_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    ge.load_package()
+    from vrt_b200 import bands as B
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = _StandInRenderer(rank, fail_open_on)
+    peer = B.PeerImage(r, 64, 32, rank, world, dist, torch)
+    if peer.ok:
+        peer.complete()  # the frame's barrier
+    state = f"{int(peer.ok)} {peer.ptr} {len(r.closed)}"
+    peer.close()
+    with open(os.path.join(result_dir, f"{rank}.txt"), "w") as f:
+        f.write(state + f" {len(r.closed)}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_open_on", [-1, 2])
+def test_peer_image_protocol_gloo(fail_open_on, tmp_path):
+    """Every rank maps rank 0's image, or -- if a single rank cannot -- every rank agrees to keep the gather path and gives
+    its mapping back (bands.PeerImage)."""
+    import torch.multiprocessing as mp
+
+    world = 3
+    mp.spawn(_peer_worker, args=(world, _free_port(), fail_open_on, str(tmp_path)), nprocs=world, join=True)
+    rows = [open(tmp_path / f"{r}.txt").read().split() for r in range(world)]
+    if fail_open_on < 0:
+        assert [row[0] for row in rows] == ["1"] * world
+        assert [int(row[1]) for row in rows] == [0x1000, 0x2001, 0x2002]
+        assert [row[3] for row in rows] == ["1"] * world  # closed exactly once, at close()
+    else:
+        assert [row[0] for row in rows] == ["0"] * world
+        assert [int(row[1]) for row in rows] == [0, 0, 0]
+        # ranks that had mapped (or created) the image released it as soon as the group agreed it is unusable
+        assert [row[2] for row in rows] == ["1", "1", "0"]
