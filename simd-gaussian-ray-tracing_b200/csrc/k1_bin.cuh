@@ -233,6 +233,8 @@ struct LeafArgs
     unsigned long long *cursor; // entries reserved so far (64-bit: a wrap past 2^32 is seen, not silently reused)
     uint64_t idx_cap;
     uint32_t n_cells;
+    uint8_t *list_wide; // per cell: 1 = a long list whose band is most of the list (see queue_key)
+    float wide_frac;
 };
 
 template <int SRC>
@@ -335,9 +337,42 @@ __global__ void __launch_bounds__(LEAF_WARPS * 32) k1_leaf(const FrameGeom G, co
             }
         }
     }
+    // How wide is the band of a long list?  For its middle entry as the emitter (samples mu - 4 sigma .. mu), count the entries
+    // whose erf argument is not saturated everywhere (|t| < 5.5 somewhere): in depth, centre within 5.5 sqrt2 sigma_j.  When that is
+    // most of the list the banded kernels have nothing to skip and the cell is queued for k2_render's in-loop test instead.
+    // A pure function of the cell's list: the bands of a frame take the same decision as the whole frame.
+    uint32_t wide = 0;
+    if (n > (uint32_t)WIN_CAP && n <= (uint32_t)LONG_CAP_KEY && (unsigned long long)off + n <= L.idx_cap)
+    {
+        __syncwarp();
+        float d[3];
+        {
+            const float u = -1.f + ((float)x0 + 0.5f * (float)(cw - 1)) / G.half_w, v = -1.f + ((float)y0 + 0.5f * (float)(ch - 1)) / G.half_h;
+            for (int i = 0; i < 3; ++i) d[i] = (G.inv0[i] * u + G.inv1[i] * v) + G.inv3[i] - G.origin[i];
+            const float inv = rsqrtf(fmaxf(dot3(d, d), 1e-30f));
+            for (int i = 0; i < 3; ++i) d[i] *= inv;
+        }
+        const float4 am = L.cullrec[2 * L.list_idx[off + n / 2]];
+        const float hi = depth_key(am, d), lo = hi - 4.f * am.w;
+        uint32_t open = 0;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32)
+        {
+            const uint32_t i = i0 + lane;
+            bool o = false;
+            if (i < n)
+            {
+                const float4 a = L.cullrec[2 * L.list_idx[off + i]];
+                const float k = depth_key(a, d), half = 7.7782f * a.w;
+                o = k + half > lo && k - half < hi;
+            }
+            open += __popc(__ballot_sync(0xffffffffu, o));
+        }
+        wide = (float)open > L.wide_frac * (float)n ? 1u : 0u;
+    }
     if (lane == 0)
     {
         L.list_off[cell] = off;
         L.list_cnt[cell] = n;
+        if (L.list_wide != nullptr) L.list_wide[cell] = (uint8_t)wide;
     }
 }

@@ -318,6 +318,7 @@ struct TileStats
     unsigned long long bin_entries;  // k1_bin: bin list entries needed
     int slice;                       // emitters per work item of split cells chosen for this frame (k1_pick_slice)
     int pad;
+    unsigned long long n_huge;       // queued items whose list is longer than k2_band_long's cache (they lead the queue)
 };
 
 __device__ __forceinline__ uint32_t cell_list_id(const FrameGeom &G, int cx, int cy)
@@ -355,11 +356,21 @@ __device__ __forceinline__ uint32_t cell_items(const FrameGeom &G, uint32_t n, u
     return k <= (1u << (32 - ITEM_CELL_BITS)) ? k : 1u;
 }
 
+constexpr uint32_t HIST_KEYS = 8192; // key = min(n, HIST_KEYS - 1) (queue_key); the queue is filled in descending key order
+// Queue key of a list (the queue is filled in descending key order): its length -- except that a long list K1 marked as WIDE
+// (its band is most of the list: nothing for k2_band_long to gain) is keyed beyond LONG_CAP, with the lists that do not fit
+// that kernel's cache, so that the head of the queue is exactly what k2_render's in-loop test works off.
+constexpr uint32_t WIDE_KEY_SHIFT = 4096;
+__device__ __forceinline__ uint32_t queue_key(uint32_t n, const uint8_t *__restrict__ wide, uint32_t id)
+{
+    if (wide != nullptr && n > (uint32_t)WIN_CAP && n <= (uint32_t)LONG_CAP_KEY && wide[id]) return n + WIDE_KEY_SHIFT;
+    return min(n, HIST_KEYS - 1u);
+}
+
 // COUNT_ITEMS = false: listed terms and per-row cost; true: work items per list-length key (needs the frame's slice size)
-constexpr uint32_t HIST_KEYS = 8192; // key = min(n, HIST_KEYS - 1); the queue is filled in descending key order
 template <bool COUNT_ITEMS>
 __global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_cnt, uint32_t *__restrict__ hist, TileStats *__restrict__ stats,
-                        double *__restrict__ row_cost, int cy_begin, int cy_end)
+                        double *__restrict__ row_cost, int cy_begin, int cy_end, const uint8_t *__restrict__ wide)
 {
     const int ncells = (cy_end - cy_begin) * G.ncx;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,7 +389,7 @@ __global__ void k1_hist(const FrameGeom G, const uint32_t *__restrict__ list_cnt
             if (COUNT_ITEMS)
             {
                 items = cell_items(G, n, (uint32_t)(cy * G.ncx + cx));
-                atomicAdd(&hist[min(n, HIST_KEYS - 1u)], items);
+                atomicAdd(&hist[queue_key(n, wide, id)], items);
                 split = items > 1 ? items : 0u;
             }
             else
@@ -474,12 +485,13 @@ __global__ void __launch_bounds__(1024) k1_hist_scan(uint32_t *__restrict__ hist
         const int key = HIST_KEYS - 1 - (t * PER + k);
         hist[key] = run;
         if (key == WIN_CAP) stats->n_big = run; // items with a longer list start the queue
+        if (key == LONG_CAP_KEY) stats->n_huge = run;
         run += c[k];
     }
 }
 
 __global__ void k1_order(const FrameGeom G, const uint32_t *__restrict__ list_cnt, uint32_t *__restrict__ cursor, uint32_t *__restrict__ queue, uint32_t *__restrict__ cell_slot,
-                         uint32_t *__restrict__ split_cursor, int cy_begin, int cy_end, uint32_t queue_cap)
+                         uint32_t *__restrict__ split_cursor, int cy_begin, int cy_end, uint32_t queue_cap, const uint8_t *__restrict__ wide)
 {
     const int ncells = (cy_end - cy_begin) * G.ncx;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,7 +504,7 @@ __global__ void k1_order(const FrameGeom G, const uint32_t *__restrict__ list_cn
     const uint32_t n = list_cnt[id];
     const uint32_t cell = (uint32_t)(cy * G.ncx + cx);
     const uint32_t items = cell_items(G, n, cell);
-    const uint32_t pos = atomicAdd(&cursor[min(n, HIST_KEYS - 1u)], items);
+    const uint32_t pos = atomicAdd(&cursor[queue_key(n, wide, id)], items);
     for (uint32_t k = 0; k < items; ++k)
         if (pos + k < queue_cap) queue[pos + k] = cell | (k << ITEM_CELL_BITS);
     // split cells get `items` consecutive slots of the partial-radiance buffer (the slot order is irrelevant: K3' sums a

@@ -10,6 +10,7 @@ constexpr int K2_WARPS = 8;        // warps per render CTA
 // CTA shape per variant: Q = 8 with a 3-CTA/SM target uses 4-warp CTAs (register cap 168, 12 warps/SM)
 __host__ __device__ constexpr int k2_cta_warps(int q, int minb) { return (q == 8 && minb == 3) ? 4 : K2_WARPS; }
 constexpr int STAGE = 32;          // records staged per warp per step (one per lane)
+constexpr int LONG_CAP_KEY = 832;  // = LONG_CAP (k2_long.cuh): longest list k2_band_long caches per CTA
 constexpr int WIN_CAP = 152;       // longest list the depth-window kernel caches per warp ((WIN_CAP+1) * 128 B of prefix sums)
 // Heavy cells (work ~ n^2) are split by emitter range into independent work items so one warp never owns a whole long list:
 // a cell with more than 3 x slice entries becomes ceil(n / slice) items; the partial radiances are summed in slice order.

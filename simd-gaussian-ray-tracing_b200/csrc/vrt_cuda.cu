@@ -45,6 +45,7 @@ namespace
 #include "k2_render.cuh"
 #include "k2_variant.cuh"
 #include "k2_band.cuh"
+#include "k2_long.cuh"
 #include "probes.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -74,7 +75,7 @@ struct vrt_cuda_ctx
     DevBuf bin_count, bin_off, bin_idx;   // per-Gaussian screen binning (k1_bin)
     DevBuf ccounts, coffsets, cidx;       // the lists K2 walks: entries [coffsets[l], coffsets[l] + ccounts[l]) of cidx
     DevBuf slice_dev;                     // slice size chosen on the device during the tile call
-    DevBuf hist, queue, stats, counter, rowcost, scan_tmp, cell_slot, partial;
+    DevBuf hist, queue, stats, counter, rowcost, scan_tmp, cell_slot, partial, cwide;
     DevBuf tile_centres; // 2 x 1024 floats: the reference's float-accumulated tile centres of the current frame
     DevBuf scene_info;   // K0: max |albedo| bits, non-monotone flag
     // interruption: the persistent render warps poll a word in DEVICE memory (an L2 hit per work item, not a PCIe read);
@@ -100,7 +101,9 @@ struct vrt_cuda_ctx
     bool have_lists = false;
     bool lists_from_host = false;
     bool lists_sorted = false;
-    uint32_t n_big = 0, n_split = 0;
+    uint32_t n_big = 0, n_huge = 0, n_split = 0;
+    float long_wide = 0.45f; // K1 marks a long list as wide (-> k2_render<WIN>) when its middle emitter must evaluate more than this share of it (VRT_CUDA_LONG_WIDE)
+    bool long_band = true; // lists beyond k2_band's cache go to k2_band_long (VRT_CUDA_LONG_BAND=0: to k2_render's in-loop test, as in round 1)
     FrameGeom geom{};
     uint32_t n_lists = 0;
     uint64_t n_entries = 0;
@@ -323,7 +326,7 @@ int build_queue(vrt_cuda_ctx *ctx, uint64_t queue_cap_hint)
     ctx->cy_end = cye;
     const int ncells = std::max(0, cye - cyb) * G.ncx;
     if (int rc = reserve(ctx, ctx->hist, sizeof(uint32_t) * HIST_KEYS)) return rc;
-    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 4)) return rc;
+    if (int rc = reserve(ctx, ctx->counter, sizeof(uint32_t) * 8)) return rc;
     if (int rc = reserve(ctx, ctx->rowcost, sizeof(double) * (size_t)G.ncy)) return rc;
     if (int rc = reserve(ctx, ctx->slice_dev, sizeof(int))) return rc;
     if (int rc = reserve(ctx, ctx->cell_slot, sizeof(uint32_t) * (size_t)G.ncx * G.ncy)) return rc;
@@ -335,11 +338,12 @@ int build_queue(vrt_cuda_ctx *ctx, uint64_t queue_cap_hint)
     G.slice_dev = (const int *)ctx->slice_dev.p;
     TileStats *stats = (TileStats *)ctx->stats.p;
     const uint32_t *lcnt = (const uint32_t *)ctx->ccounts.p;
+    const uint8_t *wide = (ctx->lists_sorted && G.list_kind == 0 && ctx->long_band) ? (const uint8_t *)ctx->cwide.p : nullptr;
     const int tb = 256, gb = std::max(1, (ncells + tb - 1) / tb);
     k1_list_stats<<<(ctx->n_lists + 255) / 256, 256, 0, ctx->stream>>>(lcnt, ctx->n_lists, stats);
-    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, stats, (double *)ctx->rowcost.p, cyb, cye);
+    k1_hist<false><<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, stats, (double *)ctx->rowcost.p, cyb, cye, nullptr);
     k1_pick_slice<<<1, 32, 0, ctx->stream>>>(stats, (int *)ctx->slice_dev.p, ctx->tune_slice, (double)ctx->sm_count * 12.0);
-    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, stats, nullptr, cyb, cye);
+    k1_hist<true><<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, stats, nullptr, cyb, cye, wide);
     k1_hist_scan<<<1, 1024, 0, ctx->stream>>>((uint32_t *)ctx->hist.p, stats);
     uint64_t cap = queue_cap_hint;
     if (cap == 0)
@@ -353,7 +357,7 @@ int build_queue(vrt_cuda_ctx *ctx, uint64_t queue_cap_hint)
     if (int rc = reserve(ctx, ctx->queue, sizeof(uint32_t) * (size_t)std::max<uint64_t>(cap, 1))) return rc;
     ctx->queue_cap = (uint32_t)cap;
     k1_order<<<gb, tb, 0, ctx->stream>>>(G, lcnt, (uint32_t *)ctx->hist.p, (uint32_t *)ctx->queue.p, (uint32_t *)ctx->cell_slot.p, (uint32_t *)ctx->counter.p + 2, cyb, cye,
-                                       (uint32_t)cap);
+                                       (uint32_t)cap, wide);
     ctx->launches += 6;
     CU(cudaGetLastError());
     return 0;
@@ -370,6 +374,7 @@ int finish_tile(vrt_cuda_ctx *ctx, TileStats &ts)
     ctx->n_queue = (uint32_t)std::min<unsigned long long>(ts.n_items, ctx->queue_cap);
     ctx->n_split = (uint32_t)ts.n_split;
     ctx->n_big = (uint32_t)ts.n_big;
+    ctx->n_huge = (uint32_t)ts.n_huge;
     ctx->geom.slice = ts.slice > 0 ? ts.slice : SLICE_MAX;
     return 0;
 }
@@ -407,15 +412,42 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
     const bool p = ctx->tune_pack != 0;
     if (a.window)
     {
-        // banded evaluation (depth-sorted index lists).  The queue is in descending list length, so the cells whose list
-        // does not fit the per-warp cache of k2_band lead it: they go to k2_render's in-loop saturation test, the rest
-        // to k2_band.
+        // banded evaluation (depth-sorted index lists).  The queue is in descending list length: the items whose list does not
+        // fit k2_band's per-warp cache lead it.  Those go to k2_band_long (one CTA per item, the list cached once per CTA in
+        // dynamic shared memory sized to the frame's longest list), lists beyond ITS capacity and the
+        // long lists K1 marked as wide (queued with them) to k2_render's in-loop saturation test, the rest to k2_band.
+        static_assert(LONG_CAP == LONG_CAP_KEY, "k1_hist_scan marks the queue position of the lists beyond k2_band_long's cache");
+        ctx->render_launches = 0;
         const uint32_t n_big = std::min(ctx->n_big, a.n_queue);
-        if (n_big)
+        const uint32_t n_huge = ctx->long_band ? std::min(ctx->n_huge, n_big) : n_big;
+        if (n_huge)
         {
             RenderArgs big = a;
-            big.n_queue = n_big;
+            big.n_queue = n_huge;
             launch_k2c<ERF, 8, true, 1, false, true>(ctx, big);
+            ctx->render_launches++;
+        }
+        if (n_big > n_huge)
+        {
+            const uint32_t cap = std::min<uint32_t>((uint32_t)LONG_CAP, (std::max<uint32_t>(ctx->q_max_list, WIN_CAP + 1) + 7u) & ~7u);
+            const size_t smem = (size_t)cap * LONG_ENTRY_BYTES;
+            int per_sm = 1;
+            // 4 CTAs per SM (128 registers) while four caches fit, else 3 (168 registers)
+            const bool four = 4 * (smem + 5120) <= 227u * 1024u;
+            if (four)
+            {
+                CU(cudaFuncSetAttribute(k2_band_long<ERF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band_long<ERF, 4>, LONG_WARPS * 32, smem);
+            }
+            else
+            {
+                CU(cudaFuncSetAttribute(k2_band_long<ERF, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band_long<ERF, 3>, LONG_WARPS * 32, smem);
+            }
+            if (per_sm < 1) per_sm = 1;
+            const uint32_t grid = std::max(1u, std::min(n_big - n_huge, (uint32_t)(ctx->sm_count * per_sm)));
+            if (four) k2_band_long<ERF, 4><<<grid, LONG_WARPS * 32, smem, ctx->stream>>>(a, n_huge, n_big, cap);
+            else k2_band_long<ERF, 3><<<grid, LONG_WARPS * 32, smem, ctx->stream>>>(a, n_huge, n_big, cap);
             ctx->render_launches++;
         }
         if (a.n_queue > n_big)
@@ -429,6 +461,7 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
             const uint32_t grid = std::max(1u, std::min(want, (uint32_t)(ctx->sm_count * per_sm)));
             if (ctx->tune_band_ctas == 5) k2_band<ERF, 5><<<grid, BAND_WARPS * 32, 0, ctx->stream>>>(a, n_big);
             else k2_band<ERF, 4><<<grid, BAND_WARPS * 32, 0, ctx->stream>>>(a, n_big);
+            ctx->render_launches++;
         }
         return 0;
     }
@@ -531,6 +564,8 @@ int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
     vrt_cuda_ctx *c = new vrt_cuda_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = std::getenv("VRT_CUDA_LONG_WIDE")) c->long_wide = (float)std::atof(e);
+    if (const char *e = std::getenv("VRT_CUDA_LONG_BAND")) c->long_band = std::atoi(e) != 0; // A/B knob: 0 sends long lists to k2_render<WIN>
     ctx = c;
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e2 == cudaSuccess; ++i) e2 = cudaEventCreate(&c->ev[i]);
@@ -577,7 +612,7 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
     if (ctx->abort_dev) cudaFree(ctx->abort_dev);
     DevBuf *bufs[] = {&ctx->tile_centres, &ctx->scene_info, &ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx, &ctx->bin_count, &ctx->bin_off,
-                      &ctx->bin_idx, &ctx->slice_dev, &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial,
+                      &ctx->bin_idx, &ctx->slice_dev, &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->cwide,
                       &ctx->out_image, &ctx->out_rad, &ctx->tile_aos, &ctx->tile_off, &ctx->lit_offsets, &ctx->lit_counts, &ctx->lit_idx};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -1004,6 +1039,9 @@ static int enqueue_cell_lists(vrt_cuda_ctx *ctx, const FrameGeom &G, uint64_t n_
     L.cursor = &stats->leaf_entries;
     L.idx_cap = std::min<uint64_t>(ctx->cidx.cap / sizeof(uint32_t), 0xFFFFFFF0ull);
     L.n_cells = (uint32_t)cells;
+    if (int rc = reserve(ctx, ctx->cwide, (size_t)cells)) return rc;
+    L.list_wide = (uint8_t *)ctx->cwide.p;
+    L.wide_frac = ctx->long_wide;
     const unsigned grid = (unsigned)((cells + LEAF_WARPS - 1) / LEAF_WARPS);
     if (src_tiles) k1_leaf<1><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
     else k1_leaf<0><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
@@ -1430,7 +1468,7 @@ int vrt_cuda_render_device(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint3
     a.image_vec16 = (image_dev && ((uintptr_t)image_dev & 15u) == 0 && (G.W & 3) == 0) ? 1u : 0u;
     a.quant_nearest = (frame->flags & VRT_CUDA_QUANT_NEAREST) ? 1u : 0u;
     a.alpha_from_w = (frame->flags & VRT_CUDA_ALPHA_FROM_W) ? 1u : 0u;
-    CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->counter.p, 0, sizeof(uint32_t) * 8, ctx->stream)); // [0] k2_render head, [1] k2_band, [3] k2_band_long
     CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_exec, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(&((TileStats *)ctx->stats.p)->terms_term, 0, sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -144,6 +144,10 @@ def rewrite_asm(src):
 def translate(name, src):
     src, n_launch = rewrite_launches(src)
     src, n_asm = rewrite_asm(src)
+    # dynamic shared memory: one buffer per CTA, handed out by the interpreter
+    src, n_dyn = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];", r"unsigned char *\1 = emu::dynamic_smem();", src)
+    if name == "k2_long.cuh":
+        assert n_dyn == 1, "k2_long.cuh: the dynamic shared memory declaration was not found"
     if name.endswith(".cu"):
         assert src.count("#include <cuda_runtime.h>") == 1
         src = src.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
@@ -158,6 +162,7 @@ def translate(name, src):
         assert k == 17, f"{k} C-ABI entry definitions found for the interpreter's API lock (17 expected)"
         src, k = re.subn(r"^(static int (?:set_gaussians_impl|render_host)\([^;{]*\)\n\{\n)", r"\1    emu::ApiLock emu_api_lock_;\n", src, flags=re.M)
         assert k == 2
+    assert "extern __shared__" not in src
     assert "<<<" not in src and not re.search(r"\basm\b", src), f"{name}: untranslated CUDA construct left"
     return src
 

@@ -102,6 +102,101 @@ def test_depth_window_long_lists_take_the_in_loop_test(pkg, renderer):
     assert st1["terms_saturated"] > 0
 
 
+def _renderer_with_env(V, **env):
+    """a context created under the given environment (the long-list knobs are read at vrt_cuda_create)"""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return V.Renderer(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("wide", ["2", "0.45"])
+def test_long_lists_share_one_cache_per_cta(pkg, wide):
+    """Lists beyond k2_band's per-warp cache (152 < n <= 832) take k2_band_long: one CTA per work item, the list cached once in
+    dynamic shared memory, pass A and the emitter blocks dealt to its four warps.  wide = 2: every such list stays in that
+    kernel; 0.45 (the default): K1 marks the cells whose band is most of the list and queues them for k2_render<WIN>.  Same image as the evaluation of every term;
+    same image as k2_render's in-loop test (VRT_CUDA_LONG_BAND=0, the round-1 route of such lists); split cells
+    and bands compose bit-exactly; parity against the arbiter."""
+    V = pkg.vrt
+    renderer = _renderer_with_env(V, VRT_CUDA_LONG_WIDE=wide)
+    try:
+        _long_list_checks(pkg, renderer)
+    finally:
+        renderer.close()
+
+
+def _long_list_checks(pkg, renderer):
+    V = pkg.vrt
+    W = 32
+    scene = pkg.scenes.synthetic(2000, 9, -1.0, -0.7)  # wide Gaussians: every cell lists hundreds
+    cam, origin = V.camera_t.app(W, W)
+    renderer.set_gaussians(scene)
+    flags = bound_flags(V)
+    f_all = renderer.frame(cam.view_matrix, origin, W, W, flags | V.EVAL_ALL, (4, 4), 6.0)
+    _, rad_all, st_all = renderer.frame_render(f_all, False, True)
+    assert 160 < st_all["max_list"] <= 832
+    f = renderer.frame(cam.view_matrix, origin, W, W, flags, (4, 4), 6.0)
+    img, rad, st = renderer.frame_render(f, True, True)
+    assert float(np.abs(rad - rad_all).max()) <= 1e-4 * max(1.0, float(rad_all.max()))
+    resolved = st["terms_executed"] + st["terms_saturated"] + st["terms_terminated"]
+    assert abs(resolved - st_all["terms_executed"]) <= 1e-2 * st_all["terms_executed"]
+    f_nt = renderer.frame(cam.view_matrix, origin, W, W, flags | V.NO_TERMINATE, (4, 4), 6.0)
+    _, rad_nt, st_nt = renderer.frame_render(f_nt, False, True)
+    assert st_nt["terms_terminated"] == 0 and float(np.abs(rad_nt - rad).max()) <= 2e-6
+    # the round-1 route of the same lists evaluates more of them
+    r1 = _renderer_with_env(V, VRT_CUDA_LONG_BAND="0")
+    try:
+        r1.set_gaussians(scene)
+        _, rad_r1, st_r1 = r1.frame_render(r1.frame(cam.view_matrix, origin, W, W, flags, (4, 4), 6.0), False, True)
+    finally:
+        r1.close()
+    print(f"listed {st['terms_listed']:.3e}: k2_band_long evaluates {st['terms_executed']:.3e}, k2_render<WIN> {st_r1['terms_executed']:.3e}")
+    # (no ordering of the two counts is asserted here: at 32 x 32 pixels a cell spans a large angle and k2_band's warp-uniform
+    # corner-ray bounds are loose, while k2_render<WIN> votes on the lanes' own arguments; test_teapot_* has the real ratio)
+    assert float(np.abs(rad_r1 - rad).max()) <= 1e-4 * max(1.0, float(rad_all.max()))
+    # split cells (every slice size) and bands of one slice size
+    try:
+        for sl in (8, 16, 64):
+            renderer.set_slice(sl)
+            img_s, rad_s, st_s = renderer.frame_render(f, True, True)
+            assert st_s["slice"] == sl and float(np.abs(rad_s - rad_all).max()) <= 1e-4 * max(1.0, float(rad_all.max()))
+            if sl == 16:
+                img2, rad2 = np.zeros_like(img_s), np.zeros_like(rad_s)
+                for rows in ((0, 8), (8, 20), (20, 32)):
+                    fb = renderer.frame(cam.view_matrix, origin, W, W, flags, (4, 4), 6.0, rows=rows)
+                    renderer.tile(fb)
+                    renderer.render(fb, True, True, image=img2, radiance=rad2)
+                assert np.array_equal(img_s, img2) and np.array_equal(rad_s, rad2)
+    finally:
+        renderer.set_slice(0)
+    pix = all_pixels(W, W, 7)
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1, f64="unit", near_sigmas=12)
+    check(gpu_at(rad, pix, W), ideal, "k2_band_long vs arbiter")
+    # an opaque cloud, four times as deep (an emitter's samples reach 4 sigma in front of it: only items that lie further
+    # than that behind the opaque layer can be dropped whole)
+    dense = pkg.scenes.synthetic(4000, 9, -1.0, -0.7)
+    z = dense[:, 6].copy()
+    dense[:, 4] *= (4 * z + 4) / (z + 4)
+    dense[:, 5] *= (4 * z + 4) / (z + 4)
+    dense[:, 6] = 4 * z
+    dense[:, 9] *= 40.0
+    renderer.set_gaussians(dense)
+    _, rad_e, st_e = renderer.frame_render(f, False, True)
+    _, rad_f, st_f = renderer.frame_render(f_nt, False, True)
+    print(f"opaque: evaluated {st_e['terms_executed']:.3e} + saturated {st_e['terms_saturated']:.3e} + terminated {st_e['terms_terminated']:.3e} "
+          f"of {st_e['terms_listed']:.3e}; without the exit {st_f['terms_executed']:.3e} evaluated")
+    assert 152 < st_e["max_list"] <= 832
+    assert st_e["terms_terminated"] > 0.2 * st_e["terms_listed"] and st_f["terms_terminated"] == 0
+    assert st_e["terms_executed"] < 0.8 * st_f["terms_executed"]
+    assert float(np.abs(rad_e - rad_f).max()) <= 1e-6 + 1e-6 * float(np.abs(rad_f).max())
+
+
 def test_split_cells_and_bands_small(pkg, renderer):
     """Heavy cells split into emitter slices: same image for every slice size (up to fp32 regrouping), bands of one slice
     size compose bit-exactly to the whole frame, parity against the oracle."""
