@@ -102,7 +102,7 @@ struct vrt_cuda_ctx
     bool lists_from_host = false;
     bool lists_sorted = false;
     uint32_t n_big = 0, n_huge = 0, n_split = 0;
-    float long_wide = 0.45f; // K1 marks a long list as wide (-> k2_render<WIN>) when its middle emitter must evaluate more than this share of it (VRT_CUDA_LONG_WIDE)
+    float long_wide = 0.5f; // K1 marks a long list as wide (-> k2_render<WIN>) when its middle emitter must evaluate more than this share of it (VRT_CUDA_LONG_WIDE)
     bool long_band = true; // lists beyond k2_band's cache go to k2_band_long (VRT_CUDA_LONG_BAND=0: to k2_render's in-loop test, as in round 1)
     FrameGeom geom{};
     uint32_t n_lists = 0;

@@ -116,11 +116,11 @@ def _renderer_with_env(V, **env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("wide", ["2", "0.45"])
+@pytest.mark.parametrize("wide", ["2", "0.5"])
 def test_long_lists_share_one_cache_per_cta(pkg, wide):
     """Lists beyond k2_band's per-warp cache (152 < n <= 832) take k2_band_long: one CTA per work item, the list cached once in
     dynamic shared memory, pass A and the emitter blocks dealt to its four warps.  wide = 2: every such list stays in that
-    kernel; 0.45 (the default): K1 marks the cells whose band is most of the list and queues them for k2_render<WIN>.  Same image as the evaluation of every term;
+    kernel; 0.5 (the default): K1 marks the cells whose band is most of the list and queues them for k2_render<WIN>.  Same image as the evaluation of every term;
     same image as k2_render's in-loop test (VRT_CUDA_LONG_BAND=0, the round-1 route of such lists); split cells
     and bands compose bit-exactly; parity against the arbiter."""
     V = pkg.vrt
