@@ -18,6 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), HERE]
 
 SIZES = [0, 1, 2, 7, 31, 32, 33, 63, 64, 65, 97, 130]
+# lists beyond k2_band's per-warp cache (152 entries): k2_band_long, or k2_render<WIN> for the cells K1 marks as wide
+SIZES_LONG = [153, 170, 200, 260]
 
 
 def tile_lists(scene, view, tx, ty):
@@ -30,13 +32,13 @@ def tile_lists(scene, view, tx, ty):
     return [idx[offs[t] : offs[t + 1]] for t in range(tx * ty)]
 
 
-def run_case(pkg, renderer, rng, verbose=False):
+def run_case(pkg, renderer, rng, verbose=False, sizes=SIZES, max_band_rows=None):
     from parity_util import oracle_radiance, pack_image, channel_diff_lsb
 
     V = pkg.vrt
     tx, ty = int(rng.choice([1, 1, 2, 3, 4, 5, 8])), int(rng.choice([1, 1, 2, 3, 4, 5, 8]))  # reference tiles per axis, not square
     W, H = tx * int(rng.integers(1, max(2, 72 // tx))), ty * int(rng.integers(1, max(2, 56 // ty)))
-    n = int(rng.choice(SIZES))
+    n = int(rng.choice(sizes))
     scene = pkg.scenes.synthetic(n, int(rng.integers(1, 1 << 30)), -1.3, -0.8) if n else np.zeros((0, 10), np.float32)
     cam, origin = V.camera_t.app(W, H, rotation=float(rng.uniform(-40, 40)))
     erf = int(rng.integers(0, 2))
@@ -57,6 +59,9 @@ def run_case(pkg, renderer, rng, verbose=False):
     if rng.integers(0, 2) == 0 and H > 1:
         a = int(rng.integers(0, H - 1))
         rows = (a, int(rng.integers(a + 1, H + 1)))
+    if max_band_rows is not None and H > max_band_rows:  # (long lists: the oracle's work per pixel grows with n^2)
+        a = rows[0] if rows != (0, 0) else int(rng.integers(0, H - max_band_rows + 1))
+        rows = (a, min(H, a + max_band_rows, rows[1] if rows != (0, 0) else H))
     slice_ = int(rng.choice([0, 0, 8, 16, 64]))
     bound_k = float(rng.choice([0.0, 6.0, 8.0]))  # 0 selects the default (6)
     q = int(rng.choice([0, 0, 4, 8]))
@@ -117,6 +122,7 @@ def main():
     ap.add_argument("--cases", type=int, default=60)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--emu", action="store_true", help="run against the interpreter build (VRT_EMU_LIB or tests/emu/_build)")
+    ap.add_argument("--long-cases", type=int, default=0, help="further cases with 153..260 Gaussians and thin bands (lists beyond k2_band's cache)")
     ap.add_argument("-v", action="store_true")
     a = ap.parse_args()
     import __graft_entry__ as ge
@@ -138,7 +144,10 @@ def main():
     for k in range(a.cases):
         desc, err = run_case(pkg, renderer, rng, a.v)
         worst = max(worst, err)
-    print(f"fuzz ok: {a.cases} cases, worst max-abs radiance error {worst:.3e}")
+    for k in range(a.long_cases):
+        desc, err = run_case(pkg, renderer, rng, a.v, sizes=SIZES_LONG, max_band_rows=5)
+        worst = max(worst, err)
+    print(f"fuzz ok: {a.cases + a.long_cases} cases, worst max-abs radiance error {worst:.3e}")
 
 
 if __name__ == "__main__":

@@ -148,7 +148,7 @@ def test_kernels_under_address_sanitizer(build_emu):
                  small + "test_k1_bins_cells_and_bands", "tests/test_gpu_parity.py::test_empty_scene_and_ragged_image", "tests/test_gpu_parity.py::test_row_bands_compose",
                  "tests/test_gpu_parity.py::test_scene_out_of_view_renders_black_in_every_list_mode"]
     if os.environ.get("VRT_EMU_FULL") == "1":
-        selection += [small + "test_depth_window_small", small + "test_depth_window_long_lists_take_the_in_loop_test", small + "test_register_block_and_packing_variants_small",
+        selection += [small + "test_depth_window_small", small + "test_depth_window_long_lists_take_the_in_loop_test", small + "test_long_lists_share_one_cache_per_cta", small + "test_register_block_and_packing_variants_small",
                       "tests/test_gpu_parity.py::test_config1_untiled", "tests/test_gpu_approx.py::test_variants_on_device_built_lists"]
     env = dict(os.environ, VRT_EMU="1", VRT_EMU_LIB=lib, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", *selection], cwd=ROOT, env=env, capture_output=True, text=True,
@@ -162,6 +162,12 @@ def test_kernels_under_address_sanitizer(build_emu):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_frames.py"), "--emu", "--cases", cases, "--seed", "3"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and "fuzz ok" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-3000:]
+    # lists beyond k2_band's per-warp cache, every one of them kept in k2_band_long (VRT_CUDA_LONG_WIDE=2: K1 marks none as wide),
+    # then with the default mark (most of these wide-sigma lists then take k2_render<WIN>)
+    for wide in ("2", "0.5"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_frames.py"), "--emu", "--cases", "0", "--long-cases", "200" if cases == "400" else "16",
+                            "--seed", "7"], cwd=ROOT, env=dict(env, VRT_CUDA_LONG_WIDE=wide), capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0 and "fuzz ok" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def _rank_worker(rank, world, port, lib_path, result_path):

@@ -293,6 +293,12 @@ def test_randomised_small_frames(pkg, renderer):
         _, err = fuzz_frames.run_case(pkg, renderer, rng)
         worst = max(worst, err)
     print(f"worst max-abs radiance error over 120 random frames: {worst:.3e}")
+    # 40 more with 153..260 Gaussians (lists beyond k2_band's per-warp cache: k2_band_long / k2_render<WIN>), thin bands
+    worst = 0.0
+    for _ in range(40):
+        _, err = fuzz_frames.run_case(pkg, renderer, rng, sizes=fuzz_frames.SIZES_LONG, max_band_rows=5)
+        worst = max(worst, err)
+    print(f"worst max-abs radiance error over 40 random long-list frames: {worst:.3e}")
 
 
 def test_k1_bins_cells_and_bands(pkg, renderer):
