@@ -91,6 +91,14 @@ struct vrt_cuda_ctx
     int pinned_next = 0;
     int pin_mode = 0; // opt-in (vrt_cuda_set_host_pinning): the caller promises its buffers outlive the registration
     DevBuf out_image, out_rad;
+    // Pageable caller buffers (what the reference's main hands in, main.cpp:245) without the pinning opt-in: the library keeps
+    // page-locked staging of its own.  The frame is written into `stage_out` by K3 (mapped: 16-byte stores over PCIe while the
+    // frame is computed) and copied to the caller's image by a few host threads; the scene is copied into `stage_in` by the same
+    // threads, chunk by chunk, each chunk's upload overlapping the next chunk's host copy.  The driver's own staging of a
+    // pageable cudaMemcpy runs at a third of that rate.
+    struct HostStage { void *p = nullptr; void *dev = nullptr; size_t cap = 0; };
+    HostStage stage_out, stage_in, stage_rad;
+    cudaEvent_t ev_stage = nullptr; // completion of the last upload out of stage_in
     struct PeerImage { void *ptr = nullptr; bool owned = false; };
     std::vector<PeerImage> peer_images; // vrt_cuda_peer_image_create / _open
     DevBuf tile_aos; // host-supplied tile lists (concatenated)
@@ -592,6 +600,11 @@ int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
         return VRT_CUDA_E_CUDA;
     }
     *c->abort_host = 0u;
+    if (cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(c->ev_stage, c->stream) != cudaSuccess)
+    {
+        cudaGetLastError();
+        c->ev_stage = nullptr; // (without it pageable uploads take the driver's staged copy)
+    }
     *ctx_out = c;
     return 0;
 }
@@ -610,6 +623,10 @@ void vrt_cuda_destroy(vrt_cuda_ctx *ctx)
     }
     if (ctx->abort_stream) { cudaStreamSynchronize(ctx->abort_stream); cudaStreamDestroy(ctx->abort_stream); }
     if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
+    if (ctx->stage_out.p) cudaFreeHost(ctx->stage_out.p);
+    if (ctx->stage_in.p) cudaFreeHost(ctx->stage_in.p);
+    if (ctx->stage_rad.p) cudaFreeHost(ctx->stage_rad.p);
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
     if (ctx->abort_dev) cudaFree(ctx->abort_dev);
     DevBuf *bufs[] = {&ctx->tile_centres, &ctx->scene_info, &ctx->aos, &ctx->rec, &ctx->cullrec, &ctx->ccounts, &ctx->coffsets, &ctx->cidx, &ctx->bin_count, &ctx->bin_off,
                       &ctx->bin_idx, &ctx->slice_dev, &ctx->hist, &ctx->queue, &ctx->stats, &ctx->counter, &ctx->rowcost, &ctx->scan_tmp, &ctx->cell_slot, &ctx->partial, &ctx->cwide,
@@ -666,6 +683,58 @@ int vrt_cuda_sync(vrt_cuda_ctx *ctx)
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// Page-locked staging owned by the context (grow-only).  Failure is not an error: the caller falls back to the plain copy.
+static bool reserve_stage(vrt_cuda_ctx::HostStage &st, size_t bytes)
+{
+    if (bytes <= st.cap) return true;
+    if (st.p) cudaFreeHost(st.p);
+    st = vrt_cuda_ctx::HostStage{};
+    const size_t want = bytes + bytes / 8 + 4096;
+    void *p = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(p); return false; }
+    st.p = p;
+    st.dev = d;
+    st.cap = want;
+    return true;
+}
+
+// memcpy by a few threads (one per 4 MB, at most 8): a single core moves ~10 GB/s, the staging copies want PCIe rate
+static void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw), bytes >> 22));
+    if (nt == 1) { std::memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes + nt - 1) / nt + 63) & ~(size_t)63;
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (size_t t = 1; t < nt; ++t)
+    {
+        const size_t off = std::min(bytes, t * per), len = std::min(bytes, off + per) - off;
+        if (len) th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    std::memcpy(dst, src, std::min(bytes, per));
+    for (auto &t : th) t.join();
+}
+
+// What kind of host memory is [p, p + bytes)?  Page-locked as a whole (CUDA copies from it asynchronously, kernels can be handed
+// its device alias), pageable, or MIXED: only part of it lies inside a registration -- two small heap buffers that share a page,
+// one of them registered, are enough -- which cudaMemcpy rejects ("invalid argument") and a kernel must not be pointed at.
+enum class HostKind { pageable, locked, mixed };
+static HostKind host_kind(const void *p, size_t bytes)
+{
+    if (!bytes) return HostKind::pageable;
+    const char *probe[3] = {(const char *)p, (const char *)p + bytes / 2, (const char *)p + bytes - 1};
+    int locked = 0;
+    for (const char *q : probe)
+    {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, q) == cudaSuccess && at.type == cudaMemoryTypeHost) ++locked;
+        cudaGetLastError();
+    }
+    return locked == 3 ? HostKind::locked : (locked == 0 ? HostKind::pageable : HostKind::mixed);
 }
 
 // Page-lock a caller buffer once per (pointer, size); the registration is kept until the slot is reused or the context is
@@ -816,7 +885,26 @@ static int set_gaussians_impl(vrt_cuda_ctx *ctx, const float *aos, uint64_t n, c
     CU(cudaSetDevice(ctx->device));
     if (int rc = reserve(ctx, ctx->aos, std::max<size_t>(n, 1) * 40)) return rc;
     if (n && kind == cudaMemcpyHostToDevice) pin_host(ctx, aos, n * 40);
-    if (n) CU(cudaMemcpyAsync(ctx->aos.p, aos, n * 40, kind, ctx->stream));
+    constexpr size_t STAGE_MIN = 256u << 10, STAGE_CHUNK = 8u << 20;
+    const HostKind hk = (n && kind == cudaMemcpyHostToDevice) ? host_kind(aos, n * 40) : HostKind::locked;
+    if (hk == HostKind::mixed && !(ctx->ev_stage && reserve_stage(ctx->stage_in, n * 40)))
+        return fail(ctx, VRT_CUDA_E_NOMEM, "the scene buffer is only partly page-locked and no staging buffer could be allocated");
+    if (n && kind == cudaMemcpyHostToDevice && (hk == HostKind::mixed || (n * 40 >= STAGE_MIN && hk == HostKind::pageable)) && ctx->ev_stage &&
+        reserve_stage(ctx->stage_in, n * 40))
+    {
+        // pageable scene: host threads copy it into the context's page-locked staging chunk by chunk, every chunk's upload
+        // overlaps the next chunk's host copy; `aos` is not referenced after this returns
+        CU(cudaEventSynchronize(ctx->ev_stage)); // (the previous upload out of the staging)
+        const size_t bytes = n * 40;
+        for (size_t off = 0; off < bytes; off += STAGE_CHUNK)
+        {
+            const size_t len = std::min(STAGE_CHUNK, bytes - off);
+            parallel_copy((char *)ctx->stage_in.p + off, (const char *)aos + off, len);
+            CU(cudaMemcpyAsync((char *)ctx->aos.p + off, (const char *)ctx->stage_in.p + off, len, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CU(cudaEventRecord(ctx->ev_stage, ctx->stream));
+    }
+    else if (n) CU(cudaMemcpyAsync(ctx->aos.p, aos, n * 40, kind, ctx->stream));
     // a copy out of page-locked memory is truly asynchronous: the caller may reuse `aos` as soon as this returns
     if (n && kind == cudaMemcpyHostToDevice && ctx->pin_mode) CU(cudaStreamSynchronize(ctx->stream));
     ctx->n_gauss = n;
@@ -1508,23 +1596,31 @@ static int render_host(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t 
     // Anything else is rendered into a device buffer and copied (staged by the driver when the memory is pageable).
     uint32_t *image_target = nullptr;
     float *rad_target = nullptr;
+    bool image_staged = false, rad_mixed = false;
     if (image)
     {
         pin_host(ctx, image, npix * sizeof(uint32_t));
+        const HostKind hk = host_kind(image, npix * sizeof(uint32_t));
         void *d = nullptr;
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, image) == cudaSuccess && at.type == cudaMemoryTypeHost && cudaHostGetDevicePointer(&d, image, 0) == cudaSuccess) image_target = (uint32_t *)d;
+        if (hk == HostKind::locked && cudaHostGetDevicePointer(&d, image, 0) == cudaSuccess) image_target = (uint32_t *)d;
         else cudaGetLastError();
+        if (!image_target && (hk == HostKind::mixed || (npix * sizeof(uint32_t) >= (256u << 10) && hk == HostKind::pageable)) && reserve_stage(ctx->stage_out, npix * sizeof(uint32_t)))
+        {
+            image_target = (uint32_t *)ctx->stage_out.dev; // pageable image: K3 writes the context's own mapped staging
+            image_staged = true;
+        }
+        if (!image_target && hk == HostKind::mixed) return fail(ctx, VRT_CUDA_E_NOMEM, "the image buffer is only partly page-locked and no staging buffer could be allocated");
         if (!image_target)
             if (int rc = reserve(ctx, ctx->out_image, npix * sizeof(uint32_t))) return rc;
     }
     if (radiance)
     {
         pin_host(ctx, radiance, npix * sizeof(float) * 4);
+        const HostKind hk = host_kind(radiance, npix * sizeof(float) * 4);
         void *d = nullptr;
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, radiance) == cudaSuccess && at.type == cudaMemoryTypeHost && cudaHostGetDevicePointer(&d, radiance, 0) == cudaSuccess) rad_target = (float *)d;
+        if (hk == HostKind::locked && cudaHostGetDevicePointer(&d, radiance, 0) == cudaSuccess) rad_target = (float *)d;
         else cudaGetLastError();
+        if (hk == HostKind::mixed) rad_mixed = true; // (copied through pageable scratch below: a CUDA copy into it would be refused)
         if (!rad_target)
             if (int rc = reserve(ctx, ctx->out_rad, npix * sizeof(float) * 4)) return rc;
     }
@@ -1556,8 +1652,19 @@ static int render_host(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame, uint32_t 
     const FrameGeom &G = ctx->geom;
     const size_t row0 = (size_t)G.row_begin, rows = (size_t)(G.row_end - G.row_begin);
     if (image && !image_target) CU(cudaMemcpyAsync(image + row0 * G.W, (uint32_t *)ctx->out_image.p + row0 * G.W, rows * G.W * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (radiance && !rad_target) CU(cudaMemcpyAsync(radiance + row0 * G.W * 4, (float *)ctx->out_rad.p + row0 * G.W * 4, rows * G.W * sizeof(float) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (radiance && !rad_target)
+    {
+        float *dst = radiance + row0 * G.W * 4;
+        if (rad_mixed)
+        {
+            if (!reserve_stage(ctx->stage_rad, rows * G.W * sizeof(float) * 4)) return fail(ctx, VRT_CUDA_E_NOMEM, "the radiance buffer is only partly page-locked and no staging buffer could be allocated");
+            dst = (float *)ctx->stage_rad.p;
+        }
+        CU(cudaMemcpyAsync(dst, (float *)ctx->out_rad.p + row0 * G.W * 4, rows * G.W * sizeof(float) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
+    if (radiance && !rad_target && rad_mixed) std::memcpy(radiance + row0 * G.W * 4, ctx->stage_rad.p, rows * G.W * sizeof(float) * 4);
+    if (image_staged) parallel_copy(image + row0 * G.W, (const uint32_t *)ctx->stage_out.p + row0 * G.W, rows * G.W * sizeof(uint32_t));
     return 0;
 }
 

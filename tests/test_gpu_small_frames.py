@@ -197,6 +197,46 @@ def _long_list_checks(pkg, renderer):
     assert float(np.abs(rad_e - rad_f).max()) <= 1e-6 + 1e-6 * float(np.abs(rad_f).max())
 
 
+def test_pageable_and_page_locked_host_buffers_give_the_same_frame(pkg, renderer):
+    """The host-buffer entries (`vrt_cuda_set_gaussians(host)` + `vrt_cuda_render(host image)`, what the reference's main calls
+    with its aligned_malloc image, main.cpp:245): plain pageable memory goes through the context's own page-locked staging
+    (threaded host copies; K3 writes the mapped staging), page-locked buffers (the opt-in) are read and written in place.
+    Same picture both ways, rows outside the band untouched, also when the scene changes between frames."""
+    V = pkg.vrt
+    W = 512  # 1 MB of pixels, 27 000 Gaussians = 1.08 MB: above the staging threshold (256 KB) and the registration threshold (1 MB)
+    flags = bound_flags(V)
+    cam, origin = V.camera_t.app(W, W, rotation=7.0)
+    scenes = [pkg.scenes.synthetic(27000, seed, -2.1, -1.8) for seed in (3, 4)]
+    frames, keep = {}, []
+    for mode in ("pageable", "page-locked"):
+        renderer.set_host_pinning(mode == "page-locked")
+        try:
+            for k, scene in enumerate(scenes):
+                if mode == "pageable":
+                    # a fresh copy per call, overwritten at once: nothing may refer to the caller's array after set_gaussians returns
+                    tmp = scene.copy()
+                    renderer.set_gaussians(tmp)
+                    tmp[:] = 0
+                else:
+                    renderer.set_gaussians(scene)  # (registered buffers must outlive the registration: `scenes` does)
+                img = np.full((W, W), 0xDEADBEEF, np.uint32)
+                keep.append(img)
+                f = renderer.frame(cam.view_matrix, origin, W, W, flags, (32, 32), 6.0, rows=(100, 180))
+                renderer.tile(f)
+                _, _, st = renderer.render(f, True, False, image=img)
+                assert np.all(img[:100] == 0xDEADBEEF) and np.all(img[180:] == 0xDEADBEEF) and not np.any(img[100:180] == 0xDEADBEEF)
+                frames[(mode, k)] = img
+        finally:
+            renderer.set_host_pinning(False)
+    for k in range(2):
+        assert np.array_equal(frames[("pageable", k)], frames[("page-locked", k)])
+    assert not np.array_equal(frames[("pageable", 0)], frames[("pageable", 1)])
+    # and the frame is the one the device-side entries produce
+    renderer.set_gaussians(scenes[1])
+    whole, _, _ = renderer.frame_render(renderer.frame(cam.view_matrix, origin, W, W, flags, (32, 32), 6.0, rows=(96, 184)), True, False)
+    assert channel_diff_lsb(whole[100:180], frames[("pageable", 1)][100:180]) <= 1
+
+
 def test_split_cells_and_bands_small(pkg, renderer):
     """Heavy cells split into emitter slices: same image for every slice size (up to fp32 regrouping), bands of one slice
     size compose bit-exactly to the whole frame, parity against the oracle."""
