@@ -111,6 +111,7 @@ struct vrt_cuda_ctx
     bool lists_sorted = false;
     uint32_t n_big = 0, n_huge = 0, n_split = 0;
     float long_wide = 0.5f; // K1 marks a long list as wide (-> k2_render<WIN>) when its middle emitter must evaluate more than this share of it (VRT_CUDA_LONG_WIDE)
+    int win_minb = 3; // resident CTAs per SM of k2_render<WIN>: 3 (4-warp CTAs, 12 warps/SM, 168 registers; 5-7 % faster on the OBJ scenes, same bits) or 1 (8 warps, 236 registers: round 1); VRT_CUDA_WIN_MINB
     bool long_band = true; // lists beyond k2_band's cache go to k2_band_long (VRT_CUDA_LONG_BAND=0: to k2_render's in-loop test, as in round 1)
     FrameGeom geom{};
     uint32_t n_lists = 0;
@@ -432,7 +433,8 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
         {
             RenderArgs big = a;
             big.n_queue = n_huge;
-            launch_k2c<ERF, 8, true, 1, false, true>(ctx, big);
+            if (ctx->win_minb == 3) launch_k2c<ERF, 8, true, 3, false, true>(ctx, big);
+            else launch_k2c<ERF, 8, true, 1, false, true>(ctx, big);
             ctx->render_launches++;
         }
         if (n_big > n_huge)
@@ -573,6 +575,7 @@ int vrt_cuda_create(int device, vrt_cuda_ctx **ctx_out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char *e = std::getenv("VRT_CUDA_LONG_WIDE")) c->long_wide = (float)std::atof(e);
+    if (const char *e = std::getenv("VRT_CUDA_WIN_MINB")) c->win_minb = std::atoi(e) == 1 ? 1 : 3;
     if (const char *e = std::getenv("VRT_CUDA_LONG_BAND")) c->long_band = std::atoi(e) != 0; // A/B knob: 0 sends long lists to k2_render<WIN>
     ctx = c;
     cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

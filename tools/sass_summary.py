@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "simd-gaussian-ray-tracing_b200", "csrc", "libvrt_cuda.so")
-KERNELS = ["k2_bandILi0ELi4", "k2_renderILi0ELi8ELb1ELi3ELb0ELb0", "k2_renderILi0ELi8ELb1ELi1ELb1ELb0", "k1_leafILi0", "k1_binILb0", "k1_binILb1", "k0_prepare", "k3_combine"]
+KERNELS = ["k2_bandILi0ELi4", "k2_band_longILi0ELi4", "k2_band_longILi0ELi3", "k2_renderILi0ELi8ELb1ELi3ELb0ELb0", "k2_renderILi0ELi8ELb1ELi1ELb1ELb0", "k1_leafILi0", "k1_binILb0", "k1_binILb1", "k0_prepare", "k3_combine"]
 WATCH = ["FFMA2", "FMUL2", "FFMA", "FMUL", "FADD", "MUFU.RCP", "MUFU.EX2", "LOP3", "LDS.128", "LDS", "STS", "LDG", "STG.E.128", "STG", "UBLKCP", "SYNCS", "VOTE", "REDUX", "SHFL",
          "ATOM", "RED", "BRA", "UTCMMA", "HMMA", "LDTM"]
 
