@@ -110,7 +110,7 @@ struct vrt_cuda_ctx
     bool lists_from_host = false;
     bool lists_sorted = false;
     uint32_t n_big = 0, n_huge = 0, n_split = 0;
-    float long_wide = 0.5f; // K1 marks a long list as wide (-> k2_render<WIN>) when its middle emitter must evaluate more than this share of it (VRT_CUDA_LONG_WIDE)
+    float long_wide = 0.4f; // K1 marks a long list as wide (-> k2_render<WIN>) when its middle emitter must evaluate more than this share of it (VRT_CUDA_LONG_WIDE)
     int win_minb = 3; // resident CTAs per SM of k2_render<WIN>: 3 (4-warp CTAs, 12 warps/SM, 168 registers; 5-7 % faster on the OBJ scenes, same bits) or 1 (8 warps, 236 registers: round 1); VRT_CUDA_WIN_MINB
     bool long_band = true; // lists beyond k2_band's cache go to k2_band_long (VRT_CUDA_LONG_BAND=0: to k2_render's in-loop test, as in round 1)
     FrameGeom geom{};

@@ -425,6 +425,64 @@ def test_depth_window_mode_is_the_same_image(pkg, renderer, erf):
     check(gpu_at(rad1, pix, W), ideal, f"depth-window mode vs arbiter (erf {erf})")
 
 
+def test_dense_long_lists_take_the_cta_shared_cache(pkg, renderer):
+    """A dense cloud of small Gaussians at 1024 x 1024: lists of up to ~290 entries, beyond k2_band's per-warp cache, with a
+    NARROW band (sigma << depth extent).  K1 does not mark them wide, so they run on k2_band_long: same image as the evaluation
+    of every term, far fewer terms evaluated than by k2_render<WIN> (VRT_CUDA_LONG_BAND=0, round 1's route), parity against the
+    arbiter; with the magnitudes x 20 the cloud is opaque and most listed terms are dropped by the transmittance bound.
+    The teapot is the opposite case (its band is most of the list): K1 marks its long cells wide and both routes coincide."""
+    V = pkg.vrt
+    W = 1024
+    flags = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
+    cam, origin = V.camera_t.app(W, W)
+    scene = pkg.scenes.synthetic(200_000, 11, -1.9, -1.5)
+
+    def route(env, scn, fl):
+        old = os.environ.get("VRT_CUDA_LONG_BAND")
+        os.environ["VRT_CUDA_LONG_BAND"] = env
+        try:
+            r = V.Renderer(0)
+        finally:
+            if old is None:
+                del os.environ["VRT_CUDA_LONG_BAND"]
+            else:
+                os.environ["VRT_CUDA_LONG_BAND"] = old
+        try:
+            r.set_gaussians(scn)
+            return r.frame_render(r.frame(cam.view_matrix, origin, W, W, fl, (16, 16), 6.0), True, True)
+        finally:
+            r.close()
+
+    img_l, rad_l, st_l = route("1", scene, flags)
+    img_w, rad_w, st_w = route("0", scene, flags)
+    img_a, rad_a, st_a = route("1", scene, flags | V.EVAL_ALL)
+    print(f"listed {st_l['terms_listed']:.3e} (longest list {st_l['max_list']}): k2_band_long evaluates {st_l['terms_executed']:.3e} in {st_l['ms_render']:.2f} ms, "
+          f"k2_render<WIN> {st_w['terms_executed']:.3e} in {st_w['ms_render']:.2f} ms, every term {st_a['ms_render']:.2f} ms")
+    assert 152 < st_l["max_list"] <= 832
+    assert st_l["terms_executed"] < 0.95 * st_w["terms_executed"] and st_l["terms_executed"] < 0.25 * st_a["terms_executed"]
+    assert channel_diff_lsb(img_l, img_a) <= 1 and channel_diff_lsb(img_w, img_a) <= 1
+    assert float(np.abs(rad_l - rad_a).max()) <= 2e-5 * max(1.0, float(rad_a.max()))
+    resolved = st_l["terms_executed"] + st_l["terms_saturated"] + st_l["terms_terminated"]
+    assert abs(resolved - st_a["terms_executed"]) <= 1e-2 * st_a["terms_executed"]
+    pix = all_pixels(W, W, 7919)
+    ideal = oracle_radiance(scene, cam.view_matrix, origin, W, W, pix, 1, f64="unit", near_sigmas=12)
+    check(gpu_at(rad_l, pix, W), ideal, "k2_band_long vs arbiter")
+    # opaque: whole work items behind the surface are dropped
+    dense = scene.copy()
+    dense[:, 9] *= 20.0
+    img_e, rad_e, st_e = route("1", dense, flags)
+    img_n, rad_n, st_n = route("1", dense, flags | V.NO_TERMINATE)
+    print(f"opaque: {st_e['terms_terminated']:.3e} of {st_e['terms_listed']:.3e} listed terms dropped, {st_e['ms_render']:.2f} ms against {st_n['ms_render']:.2f} ms without the exit")
+    assert st_e["terms_terminated"] > 0.4 * st_e["terms_listed"] and st_n["terms_terminated"] == 0
+    assert float(np.abs(rad_e - rad_n).max()) <= 1e-6 + 1e-6 * float(np.abs(rad_n).max())
+    # the teapot: wide band, K1 routes its long cells to k2_render<WIN> either way
+    teapot = np.load(os.path.join(GOLDEN, "teapot_gaussians.npy"))
+    img_t1, _, st_t1 = route("1", teapot, flags)
+    img_t0, _, st_t0 = route("0", teapot, flags)
+    assert st_t1["max_list"] > 152 and channel_diff_lsb(img_t1, img_t0) <= 1
+    assert abs(st_t1["terms_executed"] - st_t0["terms_executed"]) <= 0.02 * st_t0["terms_executed"]
+
+
 def test_two_contexts_render_concurrently_on_one_device(pkg, renderer):
     """The frame geometry is a kernel argument and the lists live in the context: two contexts on ONE GPU can have frames in
     flight at the same time (the reference's entries are re-entrant).  Context B tiles and renders another camera and size

@@ -1,6 +1,6 @@
 """A/B of the long-list route on one B200: k2_band_long (default, and with other thresholds of K1's wide-band mark: VRT_CUDA_LONG_WIDE) against k2_render<WIN> (VRT_CUDA_LONG_BAND=0, round 1's
 route of lists beyond k2_band's cache) on the bundled OBJ scenes and a dense synthetic frame; prints one JSON line per case.
-Usage: python tools/long_ab.py [frames]"""
+Usage: python tools/long_ab.py [frames [thresholds, comma-separated]]"""
 import json
 import os
 import sys
@@ -15,6 +15,7 @@ import __graft_entry__ as ge  # noqa: E402
 pkg = ge.load_package()
 V = pkg.vrt
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+THRESHOLDS = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0.3", "0.6", "0.8"]
 FLAGS = (V.MODE8 & ~V.LIST_MASK) | V.LIST_REFERENCE_BOUND
 
 
@@ -44,7 +45,7 @@ for name, make, W, tiles in CASES:
         scene[:, 8] = np.where(scene[:, 8] > 0, scene[:, 8], 0.05)  # the app's default sigma for OBJ vertices
     cam, origin = V.camera_t.app(W, W)
     row = {"case": name, "n": int(len(scene))}
-    for key, env, frac in (("long", "1", None), ("long@0.3", "1", "0.3"), ("long@0.6", "1", "0.6"), ("long@0.8", "1", "0.8"), ("long@all", "1", "2"), ("win", "0", None), ("all", "1", None)):
+    for key, env, frac in [("long", "1", None)] + [(f"long@{t}", "1", t) for t in THRESHOLDS] + [("long@all", "1", "2"), ("win", "0", None), ("all", "1", None)]:
         os.environ["VRT_CUDA_LONG_BAND"] = env
         os.environ.pop("VRT_CUDA_LONG_WIDE", None)
         if frac:
