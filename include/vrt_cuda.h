@@ -216,10 +216,15 @@ int vrt_cuda_render_interruptible(vrt_cuda_ctx *ctx, const vrt_cuda_frame *frame
 int vrt_cuda_abort(vrt_cuda_ctx *ctx, int on);
 
 /* Caller buffers.  The reference's callers hand in plain (pageable) memory -- `image` is simd::aligned_malloc'd once and
- * reused every frame (main.cpp:245, 338) -- which CUDA copies through a staging buffer at a fraction of the PCIe rate.
- * With pinning on, vrt_cuda_set_gaussians and vrt_cuda_render page-lock the buffer they are given (cudaHostRegister, once
- * per pointer; up to four registrations are kept) and copy at full rate.  OPT-IN, because the caller must keep such a
- * buffer alive until it turns pinning off again (which releases every registration) or destroys the context. */
+ * reused every frame (main.cpp:245, 338).  Such buffers go through page-locked staging that the context owns: the render
+ * kernel writes the frame into a mapped staging image while it is computed and host threads copy it to `image`; the scene is
+ * copied into staging by the same threads and uploaded chunk by chunk behind them (4 ms per frame on BASELINE config 5
+ * against a page-locked caller buffer; a pageable cudaMemcpy, staged by the driver, cost 7 ms).
+ * With pinning on, vrt_cuda_set_gaussians and vrt_cuda_render page-lock the buffer they are given instead (cudaHostRegister,
+ * once per pointer; up to four registrations are kept): the scene is read and the image written in place, no host copy
+ * remains.  OPT-IN, because the caller must keep such a buffer alive until it turns pinning off again (which releases every
+ * registration) or destroys the context.  A buffer that lies only partly inside a registration (small heap buffers sharing a
+ * page) is treated like a pageable one. */
 int vrt_cuda_set_host_pinning(vrt_cuda_ctx *ctx, int on);
 /* Explicit form: page-lock [p, p + bytes) (rounded out to pages) for every device of the process until vrt_cuda_unpin_buffer(p);
  * what an application that owns its image buffer for its whole run calls once (the host app does). */
