@@ -704,11 +704,11 @@ static bool reserve_stage(vrt_cuda_ctx::HostStage &st, size_t bytes)
     return true;
 }
 
-// memcpy by a few threads (one per 4 MB, at most 8): a single core moves ~10 GB/s, the staging copies want PCIe rate
+// memcpy by a few threads (one per MB, at most 12): a single core moves ~10 GB/s, the staging copies want PCIe rate
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw), bytes >> 22));
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(12, hw), bytes >> 20));
     if (nt == 1) { std::memcpy(dst, src, bytes); return; }
     const size_t per = ((bytes + nt - 1) / nt + 63) & ~(size_t)63;
     std::vector<std::thread> th;
