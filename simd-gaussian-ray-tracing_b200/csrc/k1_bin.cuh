@@ -232,7 +232,7 @@ struct LeafArgs
     uint32_t *list_off, *list_cnt, *list_idx;
     unsigned long long *cursor; // entries reserved so far (64-bit: a wrap past 2^32 is seen, not silently reused)
     uint64_t idx_cap;
-    uint32_t n_cells;
+    uint32_t cell_begin, n_cells; // cells [cell_begin, n_cells) are launched: the cell rows of the rendered band
     uint8_t *list_wide; // per cell: 1 = a long list whose band is most of the list (see queue_key)
     float wide_frac;
 };
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(LEAF_WARPS * 32) k1_leaf(const FrameGeom G, co
 {
     __shared__ unsigned long long s_kv[LEAF_WARPS][LEAF_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t cell = blockIdx.x * LEAF_WARPS + w;
+    const uint32_t cell = L.cell_begin + blockIdx.x * LEAF_WARPS + w;
     if (cell >= L.n_cells) return;
     const int cx = (int)(cell % G.ncx), cy = (int)(cell / G.ncx);
     int x0, y0, cw, ch;

@@ -1133,9 +1133,33 @@ static int enqueue_cell_lists(vrt_cuda_ctx *ctx, const FrameGeom &G, uint64_t n_
     if (int rc = reserve(ctx, ctx->cwide, (size_t)cells)) return rc;
     L.list_wide = (uint8_t *)ctx->cwide.p;
     L.wide_frac = ctx->long_wide;
-    const unsigned grid = (unsigned)((cells + LEAF_WARPS - 1) / LEAF_WARPS);
-    if (src_tiles) k1_leaf<1><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
-    else k1_leaf<0><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
+    // Only the cell rows that intersect the rendered row band are launched (a rank of an N-GPU frame pays 1/N of the leaf pass,
+    // not the launch of 65 536 CTAs that return at once); every other cell's list is empty by the memset.
+    int cyb = G.ncy, cye = 0;
+    for (int cy = 0; cy < G.ncy; ++cy)
+    {
+        const int y0 = (cy / G.cpty) * G.tile_h + (cy % G.cpty) * CELL_H;
+        const int h = std::min(CELL_H, G.tile_h - (cy % G.cpty) * CELL_H);
+        if (y0 + h > G.row_begin && y0 < G.row_end)
+        {
+            cyb = std::min(cyb, cy);
+            cye = std::max(cye, cy + 1);
+        }
+    }
+    const bool whole = cyb == 0 && cye == G.ncy;
+    if (!whole)
+    {
+        CU(cudaMemsetAsync(ctx->ccounts.p, 0, sizeof(uint32_t) * cells, ctx->stream));
+        CU(cudaMemsetAsync(ctx->coffsets.p, 0, sizeof(uint32_t) * cells, ctx->stream));
+    }
+    if (cye > cyb)
+    {
+        L.cell_begin = (uint32_t)cyb * (uint32_t)G.ncx;
+        L.n_cells = (uint32_t)cye * (uint32_t)G.ncx;
+        const unsigned grid = (unsigned)((L.n_cells - L.cell_begin + LEAF_WARPS - 1) / LEAF_WARPS);
+        if (src_tiles) k1_leaf<1><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
+        else k1_leaf<0><<<grid, LEAF_WARPS * 32, 0, ctx->stream>>>(G, L);
+    }
     ctx->launches++;
     ctx->n_lists = (uint32_t)cells;
     ctx->lists_sorted = true;
