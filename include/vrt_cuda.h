@@ -256,6 +256,13 @@ int vrt_cuda_row_costs(vrt_cuda_ctx *ctx, double *rows_out, uint32_t rows_cap, u
 int vrt_cuda_set_tuning(vrt_cuda_ctx *ctx, int emitter_block, int packed_f32x2);
 /* Resident CTAs per SM of the banded kernel: 4 (default, 128 registers) or 5 (96 registers); a benchmarking knob. */
 int vrt_cuda_set_band_tuning(vrt_cuda_ctx *ctx, int ctas_per_sm);
+/* Further A/B knobs are environment variables read once by vrt_cuda_create (they select between kernels that produce the same
+ * picture up to the order of the fp32 sums; the defaults are the measured best, profiles/r02_long_lists_ab.md):
+ *   VRT_CUDA_LONG_BAND=0      lists of 153..832 entries go to k2_render's in-loop saturation test instead of k2_band_long
+ *   VRT_CUDA_LONG_WIDE=<s>    K1 marks such a list "wide" (-> in-loop test) when its middle emitter must evaluate more than the
+ *                             share s of the list (default 0.4; >= 1: never)
+ *   VRT_CUDA_WIN_MINB=1       the in-loop test as one 8-warp CTA per SM (round 1) instead of three 4-warp CTAs
+ *   VRT_CUDA_MAX_LIST_ENTRIES lowers the 2^32 list-entry limit (so that a test can reach VRT_CUDA_E_NOMEM) */
 
 /* Work items of heavy cells.  A cell whose list is longer than 3 x slice entries is rendered as ceil(n / slice) independent
  * items (emitter ranges) whose partial radiances are summed in slice order; the fp32 result depends on the grouping, so two
