@@ -444,14 +444,17 @@ int dispatch_k2(vrt_cuda_ctx *ctx, const RenderArgs &a)
             int per_sm = 1;
             // 4 CTAs per SM (128 registers) while four caches fit, else 3 (168 registers)
             const bool four = 4 * (smem + 5120) <= 227u * 1024u;
+            // (the opt-in ceiling is a per-function, per-device setting shared by every context: always the kernel's maximum, so that
+            // two contexts with different list lengths cannot lower it under each other's launches)
+            constexpr int long_smem_max = LONG_CAP * LONG_ENTRY_BYTES;
             if (four)
             {
-                CU(cudaFuncSetAttribute(k2_band_long<ERF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute(k2_band_long<ERF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, long_smem_max));
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band_long<ERF, 4>, LONG_WARPS * 32, smem);
             }
             else
             {
-                CU(cudaFuncSetAttribute(k2_band_long<ERF, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute(k2_band_long<ERF, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, long_smem_max));
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_band_long<ERF, 3>, LONG_WARPS * 32, smem);
             }
             if (per_sm < 1) per_sm = 1;
