@@ -4,7 +4,8 @@
 
 // ------------------------------------------------------------------------------------------------
 // K2b-long: banded render of the long lists (WIN_CAP < n <= LONG_CAP) whose band is narrow (K1 marks the cells whose band is
-// most of the list -- the bundled OBJ scenes, sigma = 0.05 in a unit-sized object -- and queues them for k2_render<WIN>).
+// more than 40 % of the list -- the bundled OBJ scenes, sigma = 0.05 in an object two units deep -- and queues them for
+// k2_render<WIN>; k1_leaf in k1_bin.cuh, queue_key in k1_tile.cuh; measurements: profiles/r02_long_lists_ab.md).
 // Replaces the emitter loop of src/vrt/rt.h:209-221 and the occluder loop of rt.h:107-124, like k2_band.
 // ------------------------------------------------------------------------------------------------
 // Everything k2_band caches per list is WARP-UNIFORM (records, the four depth bounds per entry, their running extrema), so
@@ -21,7 +22,8 @@
 //            prefix sum at the window's front = whole pass-A quarters + a walk inside one quarter) and then runs k2_band's
 //            block loop unchanged: windows per pair group, uniform tests, moving prefix sums, early exit
 //   combine  the four partial radiances are added in warp order and stored (or written to the cell's partial slot)
-constexpr int LONG_CAP = 832;   // longest list cached per CTA: 65 KB of dynamic shared memory, 3 CTAs per SM
+constexpr int LONG_CAP = 832;   // longest list cached per CTA: 65 KB of dynamic shared memory, 3 CTAs per SM (4 up to ~660 entries: the
+                                // cache is sized to the frame's longest list, dispatch_k2 in vrt_cuda.cu)
 constexpr int LONG_WARPS = 4;
 constexpr int LONG_ENTRY_BYTES = 80;
 
