@@ -18,7 +18,7 @@
 //   skip     T at the item's shallowest sample bounds T at every sample of the item (T is non-increasing in s): when the
 //            bound of k2_band's early exit already holds there the whole item is dropped -- on an opaque object the items
 //            behind the surface end here, before any emitter is touched
-//   pass B   the item's emitter blocks are dealt to the warps as four contiguous runs; each warp places its window once (the
+//   pass B   the item's emitter blocks are dealt to the warps round-robin (warp w: blocks w, w + 4, ...); each warp places its window once (the
 //            prefix sum at the window's front = whole pass-A quarters + a walk inside one quarter) and then runs k2_band's
 //            block loop unchanged: windows per pair group, uniform tests, moving prefix sums, early exit
 //   combine  the four partial radiances are added in warp order and stored (or written to the cell's partial slot)
@@ -245,12 +245,15 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MINB) k2_band_long(const Rend
 
         float Lr = 0.f, Lg = 0.f, Lb = 0.f, La = 0.f;
         uint32_t exec = 0, sat = 0, term = 0;
-        // this warp's run of the item's emitter blocks
-        const uint32_t nblk = (q_end - q_begin + Q - 1) / Q;
-        const uint32_t qb = q_begin + ((uint32_t)warp * nblk / LONG_WARPS) * Q, qe = min(q_end, q_begin + ((uint32_t)(warp + 1) * nblk / LONG_WARPS) * Q);
+        // this warp's emitter blocks: every fourth one (block w, w + 4, ...).  Neighbouring blocks cost about the same, so the four
+        // warps finish together (contiguous runs left three warps waiting at the item's last barrier for 13 % of their cycles);
+        // consecutive windows of a warp still overlap -- a long list's window is several times wider than 16 emitters -- so they
+        // move the same way k2_band's do, only in larger steps
+        constexpr uint32_t STEP = LONG_WARPS * Q;
+        const uint32_t qb = q_begin + (uint32_t)warp * Q, qe = q_end;
         if (skip_item)
         {
-            if (qb < qe) term = (qe - qb) * n_alive;
+            if (warp == 0) term = (q_end - q_begin) * n_alive;
         }
         else if (qb < qe)
         {
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MINB) k2_band_long(const Rend
                 Pb = Pf;
             }
             uint32_t exit_check_at = qb;
-            for (uint32_t q0 = qb; q0 < qe; q0 += Q)
+            for (uint32_t q0 = qb; q0 < qe; q0 += STEP)
             {
                 const uint32_t n_real = min((uint32_t)Q, qe - q0);
                 float s[Q][5], acc[Q][5], wgt[Q];
@@ -331,13 +334,13 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MINB) k2_band_long(const Rend
                 if (g1) group_range(q0 + 2, n_real > 3, smin_g[1], smax_g[1]);
                 const float Smin = fminf(smin_g[0], smin_g[1]), Smax = fmaxf(smax_g[0], smax_g[1]);
                 float Smin_next = 3.0e38f;
-                if (q0 + Q < qe)
+                if (q0 + STEP < qe)
                 {
                     float lo, hi;
-                    group_range(q0 + Q, q0 + Q + 1 < qe, Smin_next, hi);
-                    if (q0 + Q + 2 < qe)
+                    group_range(q0 + STEP, q0 + STEP + 1 < qe, Smin_next, hi);
+                    if (q0 + STEP + 2 < qe)
                     {
-                        group_range(q0 + Q + 2, q0 + Q + 3 < qe, lo, hi);
+                        group_range(q0 + STEP + 2, q0 + STEP + 3 < qe, lo, hi);
                         Smin_next = fminf(Smin_next, lo);
                     }
                 }
@@ -439,8 +442,9 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MINB) k2_band_long(const Rend
                     La = fmaf(al.w, inner, La);
                     if ((uint32_t)e < n_real) lt_max = fmaxf(lt_max, l0);
                 }
-                // early termination inside the run (k2_band's test; `pe` lacks the emitters of the warps in front: conservative)
-                if (may_exit && q0 + Q < qe && q0 >= exit_check_at)
+                // early termination of this warp's remaining blocks (k2_band's test; `pe` lacks the other warps' emitters in front:
+                // conservative; S is the shallowest sample of ALL emitters behind this block, this warp's among them)
+                if (may_exit && q0 + STEP < qe && q0 >= exit_check_at)
                 {
                     const float w_rem = (etot - pe) * exit_scale * 1.01f;
                     if (__all_sync(0xffffffffu, ex2_approx(lt_max) * w_rem <= TERMINATE_EPS))
@@ -461,10 +465,10 @@ __global__ void __launch_bounds__(LONG_WARPS * 32, MINB) k2_band_long(const Rend
                         }
                         if (__all_sync(0xffffffffu, ex2_approx(lt) * w_rem <= TERMINATE_EPS))
                         {
-                            term += (qe - (q0 + Q)) * n_alive;
+                            for (uint32_t qr = q0 + STEP; qr < qe; qr += STEP) term += min((uint32_t)Q, qe - qr) * n_alive; // this warp's remaining emitters
                             break;
                         }
-                        exit_check_at = q0 + 3 * Q;
+                        exit_check_at = q0 + 3 * STEP;
                     }
                 }
             }
