@@ -715,13 +715,24 @@ static void parallel_copy(void *dst, const void *src, size_t bytes)
     if (nt == 1) { std::memcpy(dst, src, bytes); return; }
     const size_t per = ((bytes + nt - 1) / nt + 63) & ~(size_t)63;
     std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    for (size_t t = 1; t < nt; ++t)
+    size_t done_to = std::min(bytes, per); // [0, per) is this thread's share; [per, started_to) belongs to the helpers that started
+    size_t started_to = done_to;
+    try
     {
-        const size_t off = std::min(bytes, t * per), len = std::min(bytes, off + per) - off;
-        if (len) th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
+        th.reserve(nt - 1);
+        for (size_t t = 1; t < nt; ++t)
+        {
+            const size_t off = std::min(bytes, t * per), len = std::min(bytes, off + per) - off;
+            if (len) th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
+            started_to = off + len;
+        }
     }
-    std::memcpy(dst, src, std::min(bytes, per));
+    catch (...)
+    {
+        // (no thread to be had: nothing may escape through the C ABI -- this thread copies what no helper took)
+    }
+    std::memcpy(dst, src, done_to);
+    if (started_to < bytes) std::memcpy((char *)dst + started_to, (const char *)src + started_to, bytes - started_to);
     for (auto &t : th) t.join();
 }
 
