@@ -422,9 +422,8 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, MINB) k2_band(const RenderArg
             }
         }
         if (slot != NO_SLOT) args.partial[(size_t)(slot + slice) * 32 + lane] = make_float4(Lr, Lg, Lb, La); // summed by k3_combine
-        // 16-byte framebuffer stores (shuffle transpose).  Measured on BASELINE config 5, same box: 22.54 ms with them, 21.71 ms
-        // with one word per lane (the epilogue's extra live values cost more than the 24 saved store instructions per cell);
-        // kept because the north star asks for vectorised framebuffer writes and zero-copy output wants wide PCIe writes.
+        // 16-byte framebuffer stores (shuffle transpose): north star (3), and what the zero-copy output wants (wide PCIe writes).  On
+        // BASELINE config 5 they cost nothing against one word per lane (20.611 vs 20.605 ms, profiles/r02_band_ab.md).
         else store_cell(args, G, px, py, live, Lr, Lg, Lb, La);
         if (lane == 0 && exec) atomicAdd(args.terms_exec, (unsigned long long)exec * 5ull * n_live);
         if (lane == 0 && sat > exec) atomicAdd(args.terms_sat, (unsigned long long)(sat - exec) * 5ull * n_live);
