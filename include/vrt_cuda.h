@@ -266,7 +266,8 @@ int vrt_cuda_set_band_tuning(vrt_cuda_ctx *ctx, int ctas_per_sm);
 
 /* Work items of heavy cells.  A cell whose list is longer than 3 x slice entries is rendered as ceil(n / slice) independent
  * items (emitter ranges) whose partial radiances are summed in slice order; the fp32 result depends on the grouping, so two
- * renders are bit-identical only if they use the same slice.  slice = 0 (default) picks it per frame from the listed work;
+ * renders are bit-identical only if they use the same slice (8, 16, 32, 64, 128 or 256).  slice = 0 (default) picks it per frame
+ * from the listed work;
  * a multi-GPU caller that wants its gathered bands to equal a single-GPU frame bit for bit asks for the automatic choice
  * of the FULL frame at its share of the work (vrt_cuda_auto_slice after a full-frame vrt_cuda_tile, share = 1 / ranks) and
  * sets it on every rank.  A pinned slice also pins the emitter register block of the render kernel (8; otherwise chosen from

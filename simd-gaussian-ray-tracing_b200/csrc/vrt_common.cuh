@@ -14,7 +14,8 @@ constexpr int LONG_CAP_KEY = 832;  // = LONG_CAP (k2_long.cuh): longest list k2_
 constexpr int WIN_CAP = 152;       // longest list the depth-window kernel caches per warp ((WIN_CAP+1) * 128 B of prefix sums)
 // Heavy cells (work ~ n^2) are split by emitter range into independent work items so one warp never owns a whole long list:
 // a cell with more than 3 x slice entries becomes ceil(n / slice) items; the partial radiances are summed in slice order.
-constexpr int SLICE_MAX = 64;      // emitters per item of a split cell: 64 on big frames, down to 8 when a frame has too few
+constexpr int SLICE_MAX = 256;     // emitters per item of a split cell: 256 on big frames (every item repeats pass A over the whole list:
+                                   //   64 cost the 4M-Gaussian frame of profiles/r02_long_lists_ab.md 26 %), down to 8 when a frame has too few
 constexpr int SLICE_MIN = 8;       //   items to fill the machine (always a multiple of every emitter block size Q)
 constexpr int ITEM_CELL_BITS = 22; // work item = cell id | slice << 22  (4M cells, 1024 slices)
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;

@@ -669,7 +669,8 @@ int vrt_cuda_approx_table(vrt_cuda_ctx *ctx, int fn, const float *x, float *y, u
 int vrt_cuda_set_slice(vrt_cuda_ctx *ctx, int slice)
 {
     if (!ctx) return VRT_CUDA_E_INVALID;
-    if (slice != 0 && slice != 8 && slice != 16 && slice != 32 && slice != 64) return fail(ctx, VRT_CUDA_E_INVALID, "slice must be 0 (automatic), 8, 16, 32 or 64");
+    if (slice != 0 && slice != 8 && slice != 16 && slice != 32 && slice != 64 && slice != 128 && slice != 256)
+        return fail(ctx, VRT_CUDA_E_INVALID, "slice must be 0 (automatic), 8, 16, 32, 64, 128 or 256");
     ctx->tune_slice = slice;
     return 0;
 }
