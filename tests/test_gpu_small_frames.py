@@ -163,7 +163,7 @@ def _long_list_checks(pkg, renderer):
     assert float(np.abs(rad_r1 - rad).max()) <= 1e-4 * max(1.0, float(rad_all.max()))
     # split cells (every slice size) and bands of one slice size
     try:
-        for sl in (8, 16, 64):
+        for sl in (8, 16, 64, 256):  # (256: no cell of this frame is split -- the kernel stores the pixels itself, no combine pass)
             renderer.set_slice(sl)
             img_s, rad_s, st_s = renderer.frame_render(f, True, True)
             assert st_s["slice"] == sl and float(np.abs(rad_s - rad_all).max()) <= 1e-4 * max(1.0, float(rad_all.max()))
